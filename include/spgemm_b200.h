@@ -1,0 +1,207 @@
+/*
+ * spgemm_b200.h -- C ABI of libspgemm_b200.so, the B200 (sm_100a) CUDA replacement for the native
+ * library behind sparse_matrix_mult.sparse_matrix_multiply.
+ *
+ * The reference crosses Python -> C through ctypes with struct pointers
+ *   (/root/reference/include/functions.h:43-84, called from
+ *    /root/reference/sparse_matrix_mult/matrix_ops.py:195,333,346,348,351,360,362,365)
+ * and the struct layouts on the two sides disagree (matrix_def.h:17-31 `size_t` vs
+ * matrix_ops.py:26-33,44-48 `c_int`).  This ABI therefore passes plain pointers and sizes only:
+ * int32 CSR index arrays, float64 values, caller-owned output buffers, `int` status returns
+ * (0 = ok) with a thread-local message behind spgemm_b200_last_error().
+ *
+ * Which reference interface each entry point replaces is stated on the entry point.
+ * There is no CPU fallback: every compute call fails with SPGEMM_B200_ERR_CUDA when no sm_100 device
+ * is usable.
+ */
+#ifndef SPGEMM_B200_H
+#define SPGEMM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SPGEMM_B200_API __attribute__((visibility("default")))
+#else
+#define SPGEMM_B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPGEMM_B200_OK            0
+#define SPGEMM_B200_ERR_ARG       1   /* bad argument (null pointer, negative size, dimension mismatch) */
+#define SPGEMM_B200_ERR_CUDA      2   /* CUDA runtime error; see spgemm_b200_last_error() */
+#define SPGEMM_B200_ERR_OVERFLOW  3   /* result does not fit the requested index width */
+#define SPGEMM_B200_ERR_STATE     4   /* call order (e.g. copy of a freed result) */
+
+/* triple-product output modes (argument `mode` below) */
+#define SPGEMM_B200_TRIPLE_UPPER      0  /* triu(H Q H^T), zeros below: reference compute_full_matrix=0 */
+#define SPGEMM_B200_TRIPLE_REF_FULL   1  /* T + T^T - diag(T): what reference compute_full_matrix=1 returns
+                                            (src/sparse_sparse_dense.cpp:201-215 writes both halves of a full loop) */
+#define SPGEMM_B200_TRIPLE_MIRROR     2  /* upper triangle computed once, mirrored below: true symmetric result */
+
+/* Opaque handles. */
+typedef struct spgemm_b200_mat spgemm_b200_mat;        /* a CSR matrix resident in HBM            */
+typedef struct spgemm_b200_result spgemm_b200_result;  /* a sparse product C resident in HBM      */
+
+/* Per-call timing/size record of the LAST compute call on this thread's context.
+   All times are CUDA-event milliseconds on the library stream. */
+typedef struct {
+    double  ms_h2d;        /* host -> device copies of the operands                                   */
+    double  ms_analysis;   /* row-product count + binning (+ sortedness check, transpose for triple)   */
+    double  ms_symbolic;   /* sparse output: symbolic phase + scan                                    */
+    double  ms_numeric;    /* sparse output: numeric phase;  dense/triple: the one compute kernel      */
+    double  ms_post;       /* mirror / symmetrise kernels                                              */
+    double  ms_d2h;        /* device -> host copy of the result                                        */
+    double  ms_total;      /* first event to last event                                                */
+    int64_t products;      /* P = number of intermediate products (flops = 2P); triple: P1 + P2        */
+    int64_t nnz_c;         /* sparse output: nnz(C); dense/triple: rows*cols written                   */
+    int64_t bytes_min;     /* algorithmic (compulsory) bytes of the compute phase, SURVEY.md 8(d)      */
+    int32_t launches;      /* kernels launched by this library during the call                         */
+    int32_t device;        /* CUDA device ordinal used                                                 */
+} spgemm_b200_stats;
+
+/* ---- library / device ------------------------------------------------------------------------- */
+
+/* Library version string, e.g. "spgemm_b200 0.1 (sm_100a)". */
+SPGEMM_B200_API const char *spgemm_b200_version(void);
+
+/* Message of the last failing call on this thread ("" if none). */
+SPGEMM_B200_API const char *spgemm_b200_last_error(void);
+
+/* Number of visible CUDA devices (0 when there is no driver/GPU; never fails). */
+SPGEMM_B200_API int spgemm_b200_device_count(void);
+
+/* Bind the calling process to `device` (default 0 when never called): creates the stream, the
+   stream-ordered memory pool configuration and the timing events.  Replaces the reference's implicit
+   OpenMP team setup (omp_get_max_threads(), src/sparse_sparse_sparse.cpp:188-197). */
+SPGEMM_B200_API int spgemm_b200_init(int device);
+
+/* Release every cached device/pinned buffer and the stream. */
+SPGEMM_B200_API void spgemm_b200_shutdown(void);
+
+/* Timing/size record of the last compute call. */
+SPGEMM_B200_API int spgemm_b200_get_stats(spgemm_b200_stats *out);
+
+/* Pinned host memory from a size-bucketed cache (so NumPy results can be written by DMA at PCIe speed).
+   Replaces create_darray / destroy_darray (functions.h:54,45) as the owner of dense result storage. */
+SPGEMM_B200_API void *spgemm_b200_host_alloc(size_t bytes);
+SPGEMM_B200_API void  spgemm_b200_host_free(void *p);
+
+/* ---- host-buffer entry points: what matrix_ops.py binds ---------------------------------------- */
+
+/* C = A*B as CSR kept on the device; `upper_only` keeps col >= row only.
+   Replaces sparse_nosym / sparse_sym (functions.h:76,80; src/sparse_sparse_sparse.cpp:172-299,41-155),
+   sparsework_nosym / sparsework_sym (functions.h:61,65; src/sparsework.cpp:12-149,156-300) and
+   limits (functions.h:57; src/workdivision.cpp:16-89).  A is m x k, B is k x n.
+   Columns inside each row of C come out sorted ascending; numerically cancelled entries stay. */
+SPGEMM_B200_API int spgemm_b200_csr(int m, int k, int n,
+                    const int32_t *a_indptr, const int32_t *a_indices, const double *a_values,
+                    const int32_t *b_indptr, const int32_t *b_indices, const double *b_values,
+                    int upper_only, spgemm_b200_result **out);
+
+/* nnz / shape of a result. */
+SPGEMM_B200_API int64_t spgemm_b200_result_nnz(const spgemm_b200_result *r);
+SPGEMM_B200_API int     spgemm_b200_result_rows(const spgemm_b200_result *r);
+SPGEMM_B200_API int     spgemm_b200_result_cols(const spgemm_b200_result *r);
+
+/* Copy a result to caller-owned host arrays: indptr has rows+1 entries of int32 (index64 == 0; fails with
+   ERR_OVERFLOW when nnz >= 2^31) or int64 (index64 != 0); indices int32[nnz]; values double[nnz].
+   Replaces the array reads of sparsemat_to_csr (matrix_ops.py:205-228). */
+SPGEMM_B200_API int spgemm_b200_result_copy(const spgemm_b200_result *r, void *indptr, int index64,
+                            int32_t *indices, double *values);
+
+/* Free a result.  Replaces destroy_sparsemat (functions.h:43; matrix_ops.py:351). */
+SPGEMM_B200_API void spgemm_b200_result_free(spgemm_b200_result *r);
+
+/* Dense C (m x n row-major float64, host, caller-owned, fully overwritten) = A*B.
+   upper_only: keep col >= row, zeros below (reference dense_sym).  mirror (needs upper_only, m == n): copy
+   the upper triangle below the diagonal on the device before the copy out.
+   Replaces dense_nosym / dense_sym (functions.h:72,69; src/sparse_sparse_dense.cpp:79-131,13-74). */
+SPGEMM_B200_API int spgemm_b200_dense(int m, int k, int n,
+                      const int32_t *a_indptr, const int32_t *a_indices, const double *a_values,
+                      const int32_t *b_indptr, const int32_t *b_indices, const double *b_values,
+                      int upper_only, int mirror, double *c_host);
+
+/* Dense C (n x n row-major float64, host, caller-owned, fully overwritten) = H*Q*H^T with H n x k and
+   Q k x k, fused (H*Q is never materialised).  `mode` is one of SPGEMM_B200_TRIPLE_*.
+   Replaces triple_product (functions.h:84; src/sparse_sparse_dense.cpp:141-249). */
+SPGEMM_B200_API int spgemm_b200_triple(int n, int k,
+                       const int32_t *h_indptr, const int32_t *h_indices, const double *h_values,
+                       const int32_t *q_indptr, const int32_t *q_indices, const double *q_values,
+                       int mode, double *c_host);
+
+/* ---- device-resident entry points (operands already in HBM; used for handle reuse, the
+        kernel-only leg of bench.py and for row-sharded multi-GPU runs) --------------------------- */
+
+/* Upload a host CSR to the device (copies).  Replaces create_sparsemat + memmove
+   (functions.h:51; matrix_ops.py:187-202). */
+SPGEMM_B200_API int spgemm_b200_mat_upload(int rows, int cols, int64_t nnz,
+                           const int32_t *indptr, const int32_t *indices, const double *values,
+                           spgemm_b200_mat **out);
+
+/* Wrap device arrays the caller owns (e.g. torch tensors); nothing is copied or freed. */
+SPGEMM_B200_API int spgemm_b200_mat_wrap(int rows, int cols, int64_t nnz,
+                         const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                         spgemm_b200_mat **out);
+
+/* Build the CSR of X^T on the device. */
+SPGEMM_B200_API int spgemm_b200_mat_transpose(const spgemm_b200_mat *x, spgemm_b200_mat **out);
+
+SPGEMM_B200_API void spgemm_b200_mat_free(spgemm_b200_mat *m);
+
+/* Rows [row_begin, row_end) of C = A*B as a device-resident CSR result (row_end < 0 means all rows).
+   The result has row_end-row_begin rows. */
+SPGEMM_B200_API int spgemm_b200_csr_dev(const spgemm_b200_mat *a, const spgemm_b200_mat *b, int upper_only,
+                        int row_begin, int row_end, spgemm_b200_result **out);
+
+/* Device pointers of a result (valid until result_free): indptr is int64[rows+1]. */
+SPGEMM_B200_API int spgemm_b200_result_device_ptrs(const spgemm_b200_result *r, const int64_t **d_indptr,
+                                   const int32_t **d_indices, const double **d_values);
+
+/* Rows [row_begin, row_end) of the dense product into d_c (device, (row_end-row_begin) x n, row-major).
+   upper_only uses the GLOBAL row number for the col >= row test. */
+SPGEMM_B200_API int spgemm_b200_dense_dev(const spgemm_b200_mat *a, const spgemm_b200_mat *b, int upper_only,
+                          int row_begin, int row_end, double *d_c);
+
+/* Rows [row_begin, row_end) of H*Q*H^T into d_c (device, (row_end-row_begin) x n).  ht may be NULL (built
+   internally).  upper_only as above.  Mirroring/symmetrising needs the whole matrix and is done by
+   spgemm_b200_mirror_dev / spgemm_b200_symmetrize_dev on the gathered result. */
+SPGEMM_B200_API int spgemm_b200_triple_dev(const spgemm_b200_mat *h, const spgemm_b200_mat *q, const spgemm_b200_mat *ht,
+                           int upper_only, int row_begin, int row_end, double *d_c);
+
+/* In place on an n x n device matrix: C[j,i] = C[i,j] for j > i. */
+SPGEMM_B200_API int spgemm_b200_mirror_dev(double *d_c, int n);
+/* In place on an n x n device matrix: C = C + C^T - diag(C). */
+SPGEMM_B200_API int spgemm_b200_symmetrize_dev(double *d_c, int n);
+
+/* Per-row intermediate-product counts of rows of A against B (int64[rows(A)], device) and their total:
+   the flop-counting pass that replaces limits() (src/workdivision.cpp:16-89).  For the triple product pass
+   q != NULL: cost_i = P1_i + P2_i(upper) of H = a, Q = q, H^T = b.  Either output may be NULL. */
+SPGEMM_B200_API int spgemm_b200_row_costs(const spgemm_b200_mat *a, const spgemm_b200_mat *b, const spgemm_b200_mat *q,
+                          int upper_only, int64_t *d_costs, int64_t *total_host);
+
+/* Flop-balanced contiguous row partition: bounds[parts+1] (host) with bounds[0] = 0, bounds[parts] = rows,
+   chosen so every part carries ~total/parts of d_costs.  Replaces limits() for multi-GPU sharding. */
+SPGEMM_B200_API int spgemm_b200_partition(const int64_t *d_costs, int rows, int parts, int32_t *bounds_host);
+
+/* Raw device buffers from the library's stream-ordered pool (for callers without their own allocator),
+   and plain copies on the library stream (synchronous on return). */
+SPGEMM_B200_API void *spgemm_b200_device_alloc(size_t bytes);
+SPGEMM_B200_API void  spgemm_b200_device_free(void *d_ptr);
+SPGEMM_B200_API int   spgemm_b200_copy_to_host(void *host_dst, const void *d_src, size_t bytes);
+SPGEMM_B200_API int   spgemm_b200_copy_to_device(void *d_dst, const void *host_src, size_t bytes);
+
+/* Make the library launch on `stream` (a cudaStream_t; NULL restores the library's own stream). */
+SPGEMM_B200_API int spgemm_b200_set_stream(void *stream);
+
+/* Block until the library stream is idle. */
+SPGEMM_B200_API int spgemm_b200_synchronize(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SPGEMM_B200_H */

@@ -1,0 +1,305 @@
+// analysis.cu -- the passes that replace the reference's row partitioner (src/workdivision.cpp:16-89):
+// per-row intermediate-product counts, cost binning, scans, CSR transpose, sortedness check.
+#include "internal.h"
+
+namespace sb {
+
+#define SB_LAUNCH_CHECK(lc)            \
+    do {                               \
+        ++*(lc).launches;              \
+        cudaError_t e_ = cudaGetLastError(); \
+        if (e_ != cudaSuccess) return e_;    \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// Row products + symbolic binning.  Eight lanes per row of A: the gathers A.idx[p] -> B.ptr[j], B.ptr[j+1]
+// of a row are issued together; rows are short on average (10-200 entries in the BASELINE configs).
+__global__ void __launch_bounds__(256)
+k_row_products(Csr A, const int32_t* __restrict__ b_ptr, int b_cols, int row_begin, int nrows, int upper_only,
+               int64_t* __restrict__ prod, int32_t* __restrict__ nnz, int32_t* __restrict__ lists,
+               int32_t* __restrict__ cursor, unsigned long long* __restrict__ total) {
+    __shared__ int s_cnt[SYM_BINS], s_base[SYM_BINS];
+    __shared__ unsigned long long s_total;
+    if (threadIdx.x < SYM_BINS) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int gl = threadIdx.x & 7;
+    long long sum = 0;
+    int i = 0;
+    if (r < nrows) {
+        i = row_begin + r;
+        const int s = __ldg(A.ptr + i), e = __ldg(A.ptr + i + 1);
+#pragma unroll 4
+        for (int p = s + gl; p < e; p += 8) {
+            const int j = __ldg(A.idx + p);
+            sum += __ldg(b_ptr + j + 1) - __ldg(b_ptr + j);
+        }
+    }
+    sum += __shfl_xor_sync(FULL, sum, 1);
+    sum += __shfl_xor_sync(FULL, sum, 2);
+    sum += __shfl_xor_sync(FULL, sum, 4);
+
+    int bin = -1;
+    if (r < nrows && gl == 0) {
+        if (prod) prod[r] = sum;
+        long long cap = upper_only ? (long long)b_cols - i : (long long)b_cols;
+        long long u = sum < cap ? sum : cap;
+        if (u <= 0) {
+            nnz[r] = 0;
+        } else {
+            bin = u <= kWarpCap64 ? SYM_W64 : u <= kWarpCap256 ? SYM_W256 : u <= kWarpCap1K ? SYM_W1K : SYM_BITMAP;
+        }
+        if (sum) atomicAdd(&s_total, (unsigned long long)sum);
+    }
+    int local = 0;
+    if (bin >= 0) local = atomicAdd(&s_cnt[bin], 1);
+    __syncthreads();
+    if (threadIdx.x < SYM_BINS) {
+        const int c = s_cnt[threadIdx.x];
+        s_base[threadIdx.x] = c ? atomicAdd(cursor + threadIdx.x, c) : 0;
+    }
+    if (threadIdx.x == 0 && s_total) atomicAdd(total, s_total);
+    __syncthreads();
+    if (bin >= 0) lists[(size_t)bin * nrows + s_base[bin] + local] = r;
+}
+
+cudaError_t launch_row_products(const LaunchCtx& lc, const Csr& A, const Csr& B, int row_begin, int nrows,
+                                bool upper_only, int64_t* d_prod, int32_t* d_nnz, int32_t* d_lists,
+                                int32_t* d_cursor, unsigned long long* d_total) {
+    if (nrows <= 0) return cudaSuccess;
+    const int threads = 256, rows_per_block = threads / 8;
+    const int blocks = (nrows + rows_per_block - 1) / rows_per_block;
+    k_row_products<<<blocks, threads, 0, lc.stream>>>(A, B.ptr, B.cols, row_begin, nrows, upper_only ? 1 : 0, d_prod,
+                                                      d_nnz, d_lists, d_cursor, d_total);
+    SB_LAUNCH_CHECK(lc);
+    return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sortedness: a CSR has sorted rows iff every descent idx[q] > idx[q+1] sits on a row boundary.
+// counts[0] = descents anywhere, counts[1] = descents on row boundaries.
+__global__ void __launch_bounds__(256)
+k_count_descents(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, int rows, int64_t nnz,
+                 int32_t* __restrict__ counts) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int any = 0, edge = 0;
+    if (t + 1 < nnz) any = __ldg(idx + t) > __ldg(idx + t + 1);
+    if (t < rows) {
+        const int s = __ldg(ptr + t), e = __ldg(ptr + t + 1);
+        if (e > s && e < nnz) edge = __ldg(idx + e - 1) > __ldg(idx + e);
+    }
+    const unsigned m_any = __ballot_sync(FULL, any), m_edge = __ballot_sync(FULL, edge);
+    if (lane_id() == 0) {
+        if (m_any) atomicAdd(counts, __popc(m_any));
+        if (m_edge) atomicAdd(counts + 1, __popc(m_edge));
+    }
+}
+__global__ void k_sorted_flag(const int32_t* __restrict__ counts, int32_t* __restrict__ flag) {
+    *flag = counts[0] == counts[1] ? 1 : 0;
+}
+
+cudaError_t launch_check_sorted(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_flag, int32_t* d_scratch2) {
+    cudaError_t e = cudaMemsetAsync(d_scratch2, 0, 2 * sizeof(int32_t), lc.stream);
+    if (e != cudaSuccess) return e;
+    const int64_t n = nnz > X.rows ? nnz : X.rows;
+    if (n > 0) {
+        const int threads = 256;
+        const int64_t blocks = (n + threads - 1) / threads;
+        k_count_descents<<<(unsigned)blocks, threads, 0, lc.stream>>>(X.ptr, X.idx, X.rows, nnz, d_scratch2);
+        SB_LAUNCH_CHECK(lc);
+    }
+    k_sorted_flag<<<1, 1, 0, lc.stream>>>(d_scratch2, d_flag);
+    SB_LAUNCH_CHECK(lc);
+    return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Exclusive scan int32 -> OutT in three launches: tile sums, scan of <= 1024 tile sums, apply.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+k_scan_tile_sums(const int32_t* __restrict__ in, int n, int tile, int64_t* __restrict__ sums) {
+    __shared__ long long red[33];
+    const int lo = blockIdx.x * tile, hi = min(n, lo + tile);
+    long long s = 0;
+    for (int t = lo + threadIdx.x; t < hi; t += blockDim.x) s += __ldg(in + t);
+    long long total;
+    block_excl_scan<long long>(s, red, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_sums(int64_t* __restrict__ sums, int nb) {
+    __shared__ long long red[33];
+    long long v = (int)threadIdx.x < nb ? sums[threadIdx.x] : 0;
+    long long total;
+    long long ex = block_excl_scan<long long>(v, red, &total);
+    if ((int)threadIdx.x < nb) sums[threadIdx.x] = ex;
+    if (threadIdx.x == 0) sums[nb] = total;
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+k_scan_apply(const int32_t* __restrict__ in, OutT* __restrict__ out, int n, int tile, const int64_t* __restrict__ sums,
+             int nb) {
+    __shared__ long long red[33];
+    const int lo = blockIdx.x * tile, hi = min(n, lo + tile);
+    long long running = sums[blockIdx.x];
+    for (int base = lo; base < hi; base += blockDim.x) {
+        const int t = base + threadIdx.x;
+        long long v = t < hi ? __ldg(in + t) : 0;
+        long long total;
+        long long ex = block_excl_scan<long long>(v, red, &total);
+        if (t < hi) out[t] = (OutT)(running + ex);
+        running += total;
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = (OutT)sums[nb];
+}
+
+template <typename OutT>
+static cudaError_t launch_scan(const LaunchCtx& lc, const int32_t* in, OutT* out, int n, int64_t* d_tmp) {
+    if (n <= 0) {
+        return cudaMemsetAsync(out, 0, sizeof(OutT), lc.stream);
+    }
+    int tile = (n + 1023) / 1024;
+    tile = ((tile + 255) / 256) * 256;
+    if (tile < 2048) tile = 2048;
+    const int nb = (n + tile - 1) / tile;
+    k_scan_tile_sums<OutT><<<nb, 256, 0, lc.stream>>>(in, n, tile, d_tmp);
+    SB_LAUNCH_CHECK(lc);
+    k_scan_sums<<<1, 1024, 0, lc.stream>>>(d_tmp, nb);
+    SB_LAUNCH_CHECK(lc);
+    k_scan_apply<OutT><<<nb, 256, 0, lc.stream>>>(in, out, n, tile, d_tmp, nb);
+    SB_LAUNCH_CHECK(lc);
+    return cudaSuccess;
+}
+cudaError_t launch_scan_i64(const LaunchCtx& lc, const int32_t* in, int64_t* out, int n, int64_t* d_tmp) {
+    return launch_scan<int64_t>(lc, in, out, n, d_tmp);
+}
+cudaError_t launch_scan_i32(const LaunchCtx& lc, const int32_t* in, int32_t* out, int n, int64_t* d_tmp) {
+    return launch_scan<int32_t>(lc, in, out, n, d_tmp);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Numeric binning by exact row nnz (one thread per row, block-aggregated list append).
+__global__ void __launch_bounds__(256)
+k_bin_by_nnz(const int32_t* __restrict__ nnz, int nrows, int single_window, int32_t* __restrict__ lists,
+             int32_t* __restrict__ cursor) {
+    __shared__ int s_cnt[NUM_BINS], s_base[NUM_BINS];
+    if (threadIdx.x < NUM_BINS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int bin = -1;
+    if (r < nrows) {
+        const int c = __ldg(nnz + r);
+        if (c > 0) {
+            if (c <= kWarpCap64) bin = NUM_W64;
+            else if (c <= kWarpCap256) bin = NUM_W256;
+            else if (c <= kWarpCap1K) bin = NUM_W1K;
+            else if (single_window) bin = NUM_DENSE;
+            else if (c <= kBlockCap4K) bin = NUM_B4K;
+            else if (c <= kBlockCap16K) bin = NUM_B16K;
+            else bin = NUM_DENSE;
+        }
+    }
+    int local = 0;
+    if (bin >= 0) local = atomicAdd(&s_cnt[bin], 1);
+    __syncthreads();
+    if (threadIdx.x < NUM_BINS) {
+        const int c = s_cnt[threadIdx.x];
+        s_base[threadIdx.x] = c ? atomicAdd(cursor + threadIdx.x, c) : 0;
+    }
+    __syncthreads();
+    if (bin >= 0) lists[(size_t)bin * nrows + s_base[bin] + local] = r;
+}
+
+cudaError_t launch_bin_by_nnz(const LaunchCtx& lc, const int32_t* d_nnz, int nrows, bool single_window,
+                              int32_t* d_lists, int32_t* d_cursor) {
+    if (nrows <= 0) return cudaSuccess;
+    k_bin_by_nnz<<<(nrows + 255) / 256, 256, 0, lc.stream>>>(d_nnz, nrows, single_window ? 1 : 0, d_lists, d_cursor);
+    SB_LAUNCH_CHECK(lc);
+    return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CSR transpose (used for H^T of the triple product): column histogram, scan (above), scatter.
+__global__ void __launch_bounds__(256)
+k_transpose_count(const int32_t* __restrict__ idx, int64_t nnz, int32_t* __restrict__ counts) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nnz) atomicAdd(counts + __ldg(idx + t), 1);
+}
+__global__ void __launch_bounds__(256)
+k_transpose_fill(Csr X, const int32_t* __restrict__ t_ptr, int32_t* __restrict__ cursor, int32_t* __restrict__ t_idx,
+                 double* __restrict__ t_val) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int gl = threadIdx.x & 7;
+    if (r >= X.rows) return;
+    const int s = __ldg(X.ptr + r), e = __ldg(X.ptr + r + 1);
+    for (int p = s + gl; p < e; p += 8) {
+        const int c = __ldg(X.idx + p);
+        const int pos = __ldg(t_ptr + c) + atomicAdd(cursor + c, 1);
+        t_idx[pos] = r;
+        t_val[pos] = __ldg(X.val + p);
+    }
+}
+cudaError_t launch_transpose_count(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_counts) {
+    if (nnz <= 0) return cudaSuccess;
+    k_transpose_count<<<(unsigned)((nnz + 255) / 256), 256, 0, lc.stream>>>(X.idx, nnz, d_counts);
+    SB_LAUNCH_CHECK(lc);
+    return cudaSuccess;
+}
+cudaError_t launch_transpose_fill(const LaunchCtx& lc, const Csr& X, const int32_t* t_ptr, int32_t* d_cursor,
+                                  int32_t* t_idx, double* t_val) {
+    if (X.rows <= 0) return cudaSuccess;
+    const int blocks = (X.rows + 31) / 32;
+    k_transpose_fill<<<blocks, 256, 0, lc.stream>>>(X, t_ptr, d_cursor, t_idx, t_val);
+    SB_LAUNCH_CHECK(lc);
+    return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_narrow(const int64_t* __restrict__ in, int32_t* __restrict__ out, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = (int32_t)in[t];
+}
+cudaError_t launch_narrow_indptr(const LaunchCtx& lc, const int64_t* in, int32_t* out, int n) {
+    if (n <= 0) return cudaSuccess;
+    k_narrow<<<(n + 255) / 256, 256, 0, lc.stream>>>(in, out, n);
+    SB_LAUNCH_CHECK(lc);
+    return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cost of row i of the triple product H Q H^T for the flop-balanced multi-GPU split:
+//   P1_i = sum over (i,j) in H of nnz(Q[j,:])                         (expansion of H[i,:] Q)
+//   P2_i = sum over those (j,c) of nnz(H^T[c,:])                      (contraction against H^T), scaled by the
+//          fraction (n - i) / n of columns kept when only the upper triangle is computed.
+// One warp per row.
+__global__ void __launch_bounds__(256)
+k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, int64_t* __restrict__ costs) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= H.rows) return;
+    long long p1 = 0, p2 = 0;
+    expand_row_warp<false>(H, Q, __ldg(H.ptr + row), __ldg(H.ptr + row + 1), 0, 0, false, false,
+                           [&](int c, double) {
+                               ++p1;
+                               p2 += __ldg(Ht.ptr + c + 1) - __ldg(Ht.ptr + c);
+                           });
+    p1 = warp_sum(p1);
+    p2 = warp_sum(p2);
+    if (lane_id() == 0) {
+        if (upper_only) p2 = (long long)((double)p2 * (double)(H.rows - row) / (double)H.rows);
+        costs[row] = p1 + p2;
+    }
+}
+cudaError_t launch_triple_costs(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool upper_only,
+                                int64_t* d_costs) {
+    if (H.rows <= 0) return cudaSuccess;
+    k_triple_costs<<<(H.rows + 7) / 8, 256, 0, lc.stream>>>(H, Q, Ht, upper_only ? 1 : 0, d_costs);
+    SB_LAUNCH_CHECK(lc);
+    return cudaSuccess;
+}
+
+}  // namespace sb

@@ -1,0 +1,87 @@
+// internal.h -- host-side declarations shared by the .cu files of libspgemm_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace sb {
+
+// ---- bins ---------------------------------------------------------------------------------------
+// symbolic bins, by the row's upper bound u = min(P_i, columns left)
+enum { SYM_W64 = 0, SYM_W256, SYM_W1K, SYM_BITMAP, SYM_BINS };
+// numeric bins, by the row's exact nnz
+enum { NUM_W64 = 0, NUM_W256, NUM_W1K, NUM_B4K, NUM_B16K, NUM_DENSE, NUM_BINS };
+
+constexpr int kWarpCap64 = 48, kWarpCap256 = 192, kWarpCap1K = 768;   // <= 75 % load of the warp tables
+constexpr int kBlockCap4K = 3072, kBlockCap16K = 12288;               // <= 75 % load of the block tables
+constexpr int kDenseWindow = 16384;                                   // doubles per dense accumulator window
+
+struct LaunchCtx {
+    cudaStream_t stream;
+    int sm_count;
+    int* launches;      // incremented once per kernel launch
+};
+
+// ---- analysis.cu --------------------------------------------------------------------------------
+// Per-row product counts of rows [row_begin, row_begin+nrows) of A against B, symbolic binning.
+//   d_prod   : int64[nrows] or null
+//   d_nnz    : int32[nrows]; rows with no product get 0 here (they enter no bin)
+//   d_lists  : int32[SYM_BINS * nrows], bin b's rows (local ids) at d_lists + b*nrows
+//   d_cursor : int32[SYM_BINS], zeroed by the caller; ends as the bin sizes
+//   d_total  : unsigned long long, zeroed by the caller; ends as sum of products
+cudaError_t launch_row_products(const LaunchCtx& lc, const Csr& A, const Csr& B, int row_begin, int nrows,
+                                bool upper_only, int64_t* d_prod, int32_t* d_nnz, int32_t* d_lists,
+                                int32_t* d_cursor, unsigned long long* d_total);
+
+// d_flag (int32, device) = 1 when every row of X has non-decreasing column indices, else 0.
+cudaError_t launch_check_sorted(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_flag,
+                                int32_t* d_scratch2 /* int32[2], zeroed by callee */);
+
+// out[0] = 0, out[i+1] = out[i] + in[i]  (in int32[n], out OutT[n+1]); d_tmp holds >= 1025 int64.
+cudaError_t launch_scan_i64(const LaunchCtx& lc, const int32_t* in, int64_t* out, int n, int64_t* d_tmp);
+cudaError_t launch_scan_i32(const LaunchCtx& lc, const int32_t* in, int32_t* out, int n, int64_t* d_tmp);
+
+// numeric binning by exact nnz; single_window: every row beyond the warp bins goes to NUM_DENSE
+cudaError_t launch_bin_by_nnz(const LaunchCtx& lc, const int32_t* d_nnz, int nrows, bool single_window,
+                              int32_t* d_lists, int32_t* d_cursor);
+
+// CSR transpose: counts -> scan -> fill.  Rows of the transpose come out in arbitrary order.
+cudaError_t launch_transpose_count(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_counts);
+cudaError_t launch_transpose_fill(const LaunchCtx& lc, const Csr& X, const int32_t* t_ptr, int32_t* d_cursor,
+                                  int32_t* t_idx, double* t_val);
+
+cudaError_t launch_narrow_indptr(const LaunchCtx& lc, const int64_t* in, int32_t* out, int n);
+
+// cost model of the triple product rows (see spgemm_b200_row_costs)
+cudaError_t launch_triple_costs(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool upper_only,
+                                int64_t* d_costs);
+
+// ---- spgemm_sparse.cu ---------------------------------------------------------------------------
+struct SparseJob {
+    Csr A, B;
+    int row_begin, nrows;
+    bool upper_only;
+    const int32_t* d_b_sorted;   // device flag
+};
+cudaError_t launch_symbolic(const LaunchCtx& lc, const SparseJob& job, const int32_t* d_lists,
+                            const int32_t* h_counts /* host, SYM_BINS */, int32_t* d_nnz, int32_t* d_work_counter);
+cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int32_t* d_lists,
+                           const int32_t* h_counts /* host, NUM_BINS */, const int64_t* c_ptr, int32_t* c_idx,
+                           double* c_val, int32_t* d_work_counter);
+cudaError_t sparse_kernels_configure();
+
+// ---- spgemm_dense.cu ----------------------------------------------------------------------------
+cudaError_t launch_dense(const LaunchCtx& lc, const Csr& A, const Csr& B, const int32_t* d_b_sorted,
+                         bool upper_only, int row_begin, int nrows, double* d_c);
+cudaError_t launch_mirror(const LaunchCtx& lc, double* d_c, int n);
+cudaError_t launch_symmetrize(const LaunchCtx& lc, double* d_c, int n);
+cudaError_t dense_kernels_configure();
+
+// ---- triple.cu ----------------------------------------------------------------------------------
+cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht,
+                          bool upper_only, int row_begin, int nrows, double* d_c,
+                          unsigned long long* d_counters /* [2]: P1, P2; may be null */);
+cudaError_t triple_kernels_configure();
+
+}  // namespace sb

@@ -1,0 +1,197 @@
+"""Device-resident handles over libspgemm_b200.so: operands stay in HBM across calls.
+
+Used by bench.py's kernel-only leg, by the multi-GPU row-sharded driver (distributed.py) and by callers that
+iterate on the same matrices.  Thin ctypes wrappers; every method maps to one entry point of
+include/spgemm_b200.h.
+"""
+import ctypes
+
+import numpy as np
+from scipy.sparse import csr_matrix, isspmatrix_csr
+
+from .matrix_ops import _check, _f64p, _i32p, _ptrs, _vp, csr_to_arrays, last_stats, matrix_ops, result_to_csr
+
+__all__ = ["DeviceMatrix", "DeviceResult", "DeviceDense", "spgemm_csr", "spgemm_dense", "triple_product",
+           "row_costs", "partition_rows", "last_stats", "set_stream", "synchronize", "init"]
+
+
+def init(device=0):
+    _check(matrix_ops.get_lib().spgemm_b200_init(int(device)), "spgemm_b200_init")
+
+
+def set_stream(stream_ptr):
+    """Launch on a caller stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None restores the own stream."""
+    _check(matrix_ops.get_lib().spgemm_b200_set_stream(_vp(stream_ptr or 0)), "spgemm_b200_set_stream")
+
+
+def synchronize():
+    _check(matrix_ops.get_lib().spgemm_b200_synchronize(), "spgemm_b200_synchronize")
+
+
+class DeviceMatrix:
+    """A CSR matrix in HBM (int32 indices, float64 values)."""
+
+    def __init__(self, handle, shape, nnz, keep=None):
+        self._h, self.shape, self.nnz, self._keep = handle, tuple(shape), int(nnz), keep
+
+    @classmethod
+    def from_scipy(cls, x):
+        if not isspmatrix_csr(x):
+            x = csr_matrix(x)
+        arrs = csr_to_arrays(x)
+        h = _vp()
+        _check(matrix_ops.get_lib().spgemm_b200_mat_upload(x.shape[0], x.shape[1], x.nnz, *_ptrs(arrs),
+                                                           ctypes.byref(h)), "spgemm_b200_mat_upload")
+        return cls(h, x.shape, x.nnz)
+
+    @classmethod
+    def wrap(cls, shape, nnz, indptr_ptr, indices_ptr, values_ptr, keep=None):
+        """Borrow device arrays (raw addresses, e.g. tensor.data_ptr()); `keep` holds their owners alive."""
+        h = _vp()
+        _check(matrix_ops.get_lib().spgemm_b200_mat_wrap(shape[0], shape[1], nnz, _vp(indptr_ptr), _vp(indices_ptr),
+                                                         _vp(values_ptr), ctypes.byref(h)), "spgemm_b200_mat_wrap")
+        return cls(h, shape, nnz, keep)
+
+    def transpose(self):
+        h = _vp()
+        _check(matrix_ops.get_lib().spgemm_b200_mat_transpose(self._h, ctypes.byref(h)), "spgemm_b200_mat_transpose")
+        return DeviceMatrix(h, self.shape[::-1], self.nnz)
+
+    def free(self):
+        if self._h:
+            matrix_ops.get_lib().spgemm_b200_mat_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceResult:
+    """A sparse product in HBM: int64 indptr, int32 indices (sorted), float64 values."""
+
+    def __init__(self, handle):
+        lib = matrix_ops.get_lib()
+        self._h = handle
+        self.shape = (lib.spgemm_b200_result_rows(handle), lib.spgemm_b200_result_cols(handle))
+        self.nnz = int(lib.spgemm_b200_result_nnz(handle))
+
+    def device_ptrs(self):
+        p, i, v = _vp(), _vp(), _vp()
+        _check(matrix_ops.get_lib().spgemm_b200_result_device_ptrs(self._h, ctypes.byref(p), ctypes.byref(i),
+                                                                   ctypes.byref(v)), "result_device_ptrs")
+        return p.value, i.value, v.value
+
+    def to_scipy(self):
+        return result_to_csr(matrix_ops.get_lib(), self._h, self.shape)
+
+    def indptr_host(self):
+        out = np.empty(self.shape[0] + 1, dtype=np.int64)
+        p, _, _ = self.device_ptrs()
+        _check(matrix_ops.get_lib().spgemm_b200_copy_to_host(out.ctypes.data_as(_vp), _vp(p), out.nbytes), "copy_to_host")
+        return out
+
+    def free(self):
+        if self._h:
+            matrix_ops.get_lib().spgemm_b200_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceDense:
+    """rows x cols float64 row-major buffer in HBM from the library's pool."""
+
+    def __init__(self, rows, cols):
+        self.shape = (int(rows), int(cols))
+        self.nbytes = self.shape[0] * self.shape[1] * 8
+        self.ptr = matrix_ops.get_lib().spgemm_b200_device_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError(matrix_ops.get_lib().spgemm_b200_last_error().decode(errors="replace"))
+
+    def to_host(self, out=None):
+        if out is None:
+            out = np.empty(self.shape, dtype=np.float64)
+        _check(matrix_ops.get_lib().spgemm_b200_copy_to_host(out.ctypes.data_as(_vp), _vp(self.ptr), self.nbytes),
+               "copy_to_host")
+        return out
+
+    def free(self):
+        if self.ptr:
+            matrix_ops.get_lib().spgemm_b200_device_free(_vp(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _rows(a, row_begin, row_end):
+    if row_end is None:
+        return 0, a.shape[0]
+    return int(row_begin), int(row_end)
+
+
+def spgemm_csr(a, b, upper_only=False, row_begin=0, row_end=None):
+    r0, r1 = _rows(a, row_begin, row_end)
+    h = _vp()
+    _check(matrix_ops.get_lib().spgemm_b200_csr_dev(a._h, b._h, int(bool(upper_only)), r0, r1, ctypes.byref(h)),
+           "spgemm_b200_csr_dev")
+    return DeviceResult(h)
+
+
+def spgemm_dense(a, b, upper_only=False, row_begin=0, row_end=None, out=None):
+    r0, r1 = _rows(a, row_begin, row_end)
+    if out is None:
+        out = DeviceDense(r1 - r0, b.shape[1])
+    ptr = out.ptr if isinstance(out, DeviceDense) else int(out)
+    _check(matrix_ops.get_lib().spgemm_b200_dense_dev(a._h, b._h, int(bool(upper_only)), r0, r1, _vp(ptr)),
+           "spgemm_b200_dense_dev")
+    return out
+
+
+def triple_product(h, q, ht=None, upper_only=True, row_begin=0, row_end=None, out=None):
+    r0, r1 = _rows(h, row_begin, row_end)
+    if out is None:
+        out = DeviceDense(r1 - r0, h.shape[0])
+    ptr = out.ptr if isinstance(out, DeviceDense) else int(out)
+    _check(matrix_ops.get_lib().spgemm_b200_triple_dev(h._h, q._h, ht._h if ht is not None else None,
+                                                       int(bool(upper_only)), r0, r1, _vp(ptr)),
+           "spgemm_b200_triple_dev")
+    return out
+
+
+def mirror(out, n):
+    ptr = out.ptr if isinstance(out, DeviceDense) else int(out)
+    _check(matrix_ops.get_lib().spgemm_b200_mirror_dev(_vp(ptr), int(n)), "spgemm_b200_mirror_dev")
+
+
+def symmetrize(out, n):
+    ptr = out.ptr if isinstance(out, DeviceDense) else int(out)
+    _check(matrix_ops.get_lib().spgemm_b200_symmetrize_dev(_vp(ptr), int(n)), "spgemm_b200_symmetrize_dev")
+
+
+def row_costs(a, b, q=None, upper_only=False):
+    """(device buffer of int64 per-row costs, total).  Sparse/dense: a=A, b=B.  Triple: a=H, b=H^T, q=Q."""
+    lib = matrix_ops.get_lib()
+    d = lib.spgemm_b200_device_alloc(max(1, a.shape[0]) * 8)
+    total = ctypes.c_int64(0)
+    _check(lib.spgemm_b200_row_costs(a._h, b._h, q._h if q is not None else None, int(bool(upper_only)), _vp(d),
+                                     ctypes.byref(total)), "spgemm_b200_row_costs")
+    return d, int(total.value)
+
+
+def partition_rows(d_costs, rows, parts):
+    """Flop-balanced contiguous row bounds (len parts+1) -- the multi-GPU replacement of limits()."""
+    out = np.zeros(parts + 1, dtype=np.int32)
+    _check(matrix_ops.get_lib().spgemm_b200_partition(_vp(d_costs), int(rows), int(parts),
+                                                      out.ctypes.data_as(_i32p)), "spgemm_b200_partition")
+    return out

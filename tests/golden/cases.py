@@ -12,7 +12,6 @@ duplicate entries, exact cancellation (explicit zeros kept), rectangular shapes,
 Only numpy/scipy generators with fixed seeds: the same arrays come out on the GPU box.
 """
 import numpy as np
-from scipy import stats
 from scipy.sparse import csr_matrix, diags, random as sparse_random
 
 MODES = {
@@ -58,8 +57,11 @@ def fixed_matrices():
 
 
 def seeded_pair(n=120, density=0.3):
-    a = csr_matrix(sparse_random(n, n, density=density, random_state=42, data_rvs=stats.uniform().rvs))
-    b = csr_matrix(sparse_random(n, n, density=density, random_state=43, data_rvs=stats.uniform().rvs))
+    # the reference draws the VALUES from SciPy's unseeded global stream (data_rvs=stats.uniform().rvs);
+    # here they are seeded too so that the fixture is reproducible
+    a = csr_matrix(sparse_random(n, n, density=density, random_state=42,
+                                 data_rvs=np.random.default_rng(142).random))
+    b = csr_matrix(sparse_random(n, n, density=density, random_state=43, data_rvs=np.random.default_rng(143).random))
     return a, b
 
 
