@@ -197,6 +197,14 @@ SPGEMM_B200_API int   spgemm_b200_copy_to_device(void *d_dst, const void *host_s
 /* Make the library launch on `stream` (a cudaStream_t; NULL restores the library's own stream). */
 SPGEMM_B200_API int spgemm_b200_set_stream(void *stream);
 
+/* CUDA-event stopwatch on the library stream: start records an event, stop records another, waits for it and
+   returns the milliseconds in between (what bench.py brackets each step with). */
+SPGEMM_B200_API int spgemm_b200_timer_start(void);
+SPGEMM_B200_API int spgemm_b200_timer_stop(double *ms);
+
+/* Overwrite a scratch buffer larger than the L2 cache (evicts operands between timed iterations). */
+SPGEMM_B200_API int spgemm_b200_flush_l2(void);
+
 /* Block until the library stream is idle. */
 SPGEMM_B200_API int spgemm_b200_synchronize(void);
 

@@ -728,6 +728,35 @@ int spgemm_b200_copy_to_device(void* d_dst, const void* host_src, size_t bytes) 
     return SPGEMM_B200_OK;
 }
 
+// ---- stopwatch / L2 flush ------------------------------------------------------------------------------------
+static cudaEvent_t t_ev0 = nullptr, t_ev1 = nullptr;
+static void* g_flush_buf = nullptr;
+static const size_t kFlushBytes = (size_t)512 << 20;
+
+int spgemm_b200_timer_start(void) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!t_ev0) { CU(cudaEventCreate(&t_ev0)); CU(cudaEventCreate(&t_ev1)); }
+    CU(cudaEventRecord(t_ev0, g.stream));
+    return SPGEMM_B200_OK;
+}
+int spgemm_b200_timer_stop(double* ms) {
+    if (!g.ready || !t_ev0) return fail(SPGEMM_B200_ERR_STATE, "timer_stop without timer_start");
+    CU(cudaEventRecord(t_ev1, g.stream));
+    CU(cudaEventSynchronize(t_ev1));
+    float f = 0.f;
+    CU(cudaEventElapsedTime(&f, t_ev0, t_ev1));
+    if (ms) *ms = f;
+    return SPGEMM_B200_OK;
+}
+int spgemm_b200_flush_l2(void) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!g_flush_buf) CU(cudaMalloc(&g_flush_buf, kFlushBytes));
+    CU(cudaMemsetAsync(g_flush_buf, 0x5a, kFlushBytes, g.stream));
+    return SPGEMM_B200_OK;
+}
+
 // ---- row costs / partition ------------------------------------------------------------------------------
 int spgemm_b200_row_costs(const spgemm_b200_mat* a, const spgemm_b200_mat* b, const spgemm_b200_mat* q, int upper_only,
                           int64_t* d_costs, int64_t* total_host) {

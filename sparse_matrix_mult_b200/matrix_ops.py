@@ -111,6 +111,7 @@ class MatrixOpsLibrary:
         L.spgemm_b200_copy_to_host.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.spgemm_b200_copy_to_device.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.spgemm_b200_set_stream.argtypes = [_vp]
+        L.spgemm_b200_timer_stop.argtypes = [ctypes.POINTER(ctypes.c_double)]
 
     def get_lib(self):
         if self._lib is None:
