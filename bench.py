@@ -333,7 +333,9 @@ def run_ours(args, w, name, info, flops, rank, world):
 
     # ---- end to end through the public API (host operands in pinned memory, host result) ---------------
     e2e = None
-    if world == 1:
+    if args.no_e2e:
+        pass
+    elif world == 1:
         ap = pinned_csr(a)
         bp = ap if (b is a) else pinned_csr(b)
         for _ in range(min(2, args.warmup)):
@@ -395,6 +397,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

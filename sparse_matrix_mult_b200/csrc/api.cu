@@ -84,6 +84,12 @@ int ensure_init() {
 
 LaunchCtx lctx() { return LaunchCtx{g.stream, g.sm_count, &g.launches}; }
 
+// kernel-variant overrides for experiments: SPGEMM_B200_DENSE_MODE / SPGEMM_B200_TRIPLE_MODE = 0 auto, 1 smem, 2 red
+int env_mode(const char* name) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : 0;
+}
+
 template <typename T>
 int dalloc(T** p, size_t count) {
     *p = nullptr;
@@ -97,6 +103,14 @@ void dfree(void* p) {
 Csr view(const spgemm_b200_mat* m) { return Csr{m->ptr, m->idx, m->val, m->rows, m->cols}; }
 
 int64_t csr_bytes(int64_t rows, int64_t nnz) { return 12 * nnz + 4 * (rows + 1); }
+
+// estimate of products per output element from the operand sizes alone (no pass over the data):
+// P ~ nnz(A) * nnz(B) / rows(B)
+double products_per_out(const spgemm_b200_mat* a, const spgemm_b200_mat* b) {
+    const double out = (double)a->rows * (double)b->cols;
+    if (out <= 0 || b->rows <= 0) return 0.0;
+    return (double)a->nnz * ((double)b->nnz / (double)b->rows) / out;
+}
 
 void begin_call() {
     g.launches = 0;
@@ -552,7 +566,8 @@ int spgemm_b200_dense_dev(const spgemm_b200_mat* a, const spgemm_b200_mat* b, in
     mark(EV_H2D);
     if ((rc = ensure_sorted_flag(const_cast<spgemm_b200_mat*>(b)))) return rc;
     mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
-    CU(launch_dense(lctx(), view(a), view(b), b->d_sorted, upper_only != 0, row_begin, row_end - row_begin, d_c));
+    CU(launch_dense(lctx(), view(a), view(b), b->d_sorted, upper_only != 0, row_begin, row_end - row_begin, d_c,
+                    env_mode("SPGEMM_B200_DENSE_MODE"), products_per_out(a, b)));
     mark(EV_NUMERIC); mark(EV_POST); mark(EV_D2H);
     g.stats.nnz_c = (int64_t)(row_end - row_begin) * b->cols;
     g.stats.bytes_min = csr_bytes(a->rows, a->nnz) + csr_bytes(b->rows, b->nnz) + 8 * g.stats.nnz_c;
@@ -582,7 +597,8 @@ int spgemm_b200_dense(int m, int k, int n, const int32_t* a_indptr, const int32_
     mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
     const size_t elems = (size_t)m * (size_t)n;
     if ((rc = dalloc(&d_c, elems))) return done(rc);
-    cudaError_t e = launch_dense(lctx(), view(a), view(b), b->d_sorted, upper_only != 0, 0, m, d_c);
+    cudaError_t e = launch_dense(lctx(), view(a), view(b), b->d_sorted, upper_only != 0, 0, m, d_c,
+                                 env_mode("SPGEMM_B200_DENSE_MODE"), products_per_out(a, b));
     if (e != cudaSuccess) return done(fail(SPGEMM_B200_ERR_CUDA, "dense kernel", e));
     mark(EV_NUMERIC);
     if (mirror) {
@@ -623,7 +639,8 @@ int spgemm_b200_triple_dev(const spgemm_b200_mat* h, const spgemm_b200_mat* q, c
     if ((rc = dalloc(&d_cnt, 2))) { spgemm_b200_mat_free(own_ht); return rc; }
     cudaError_t e = cudaMemsetAsync(d_cnt, 0, 16, g.stream);
     if (e == cudaSuccess)
-        e = launch_triple(lctx(), view(h), view(q), view(ht), upper_only != 0, row_begin, row_end - row_begin, d_c, d_cnt);
+        e = launch_triple(lctx(), view(h), view(q), view(ht), upper_only != 0, row_begin, row_end - row_begin, d_c, d_cnt,
+                          env_mode("SPGEMM_B200_TRIPLE_MODE"));
     mark(EV_NUMERIC); mark(EV_POST);
     unsigned long long* hc = reinterpret_cast<unsigned long long*>(static_cast<char*>(g.h_small) + 512);
     if (e == cudaSuccess) e = cudaMemcpyAsync(hc, d_cnt, 16, cudaMemcpyDeviceToHost, g.stream);
@@ -665,7 +682,7 @@ int spgemm_b200_triple(int n, int k, const int32_t* h_indptr, const int32_t* h_i
     if ((rc = dalloc(&d_c, elems)) || (rc = dalloc(&d_cnt, 2))) return done(rc);
     const bool upper = mode != SPGEMM_B200_TRIPLE_REF_FULL;
     cudaError_t e = cudaMemsetAsync(d_cnt, 0, 16, g.stream);
-    if (e == cudaSuccess) e = launch_triple(lctx(), view(h), view(q), view(ht), upper, 0, n, d_c, d_cnt);
+    if (e == cudaSuccess) e = launch_triple(lctx(), view(h), view(q), view(ht), upper, 0, n, d_c, d_cnt, env_mode("SPGEMM_B200_TRIPLE_MODE"));
     if (e != cudaSuccess) return done(fail(SPGEMM_B200_ERR_CUDA, "triple kernel", e));
     mark(EV_NUMERIC);
     if (mode == SPGEMM_B200_TRIPLE_REF_FULL) e = launch_symmetrize(lctx(), d_c, n);

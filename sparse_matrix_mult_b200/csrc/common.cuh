@@ -115,6 +115,7 @@ __device__ __forceinline__ int lower_bound(const int32_t* __restrict__ idx, int 
 // by binary search inside each row of B, otherwise every entry is read and filtered.
 // f must not contain warp-synchronous operations (lanes call it divergently).
 constexpr int kLongRow = 48;
+constexpr int kClipMin = 32;    // rows of B at most this long are filtered, longer ones binary-searched
 
 template <bool WITH_VALUES, class F>
 __device__ __forceinline__ void expand_row_warp(const Csr& A, const Csr& B, int a_begin, int a_end,
@@ -130,14 +131,14 @@ __device__ __forceinline__ void expand_row_warp(const Csr& A, const Csr& B, int 
             s = __ldg(B.ptr + j);
             int e = __ldg(B.ptr + j + 1);
             if (WITH_VALUES) av = __ldg(A.val + p);
-            if (windowed && b_sorted && e > s) {
-                // clip [s, e) to the column window
+            if (windowed && b_sorted && e - s > kClipMin) {
+                // clip [s, e) to the column window (short rows are cheaper to filter entry by entry)
                 if (__ldg(B.idx + s) < col_lo) s = lower_bound(B.idx, s, e, col_lo);
                 if (e > s && __ldg(B.idx + e - 1) >= col_hi) e = lower_bound(B.idx, s, e, col_hi);
             }
             len = e - s;
         }
-        const bool filter = windowed && !b_sorted;
+        const bool filter = windowed;
         // whole-warp pass over the long rows of B
         unsigned longmask = __ballot_sync(FULL, len >= kLongRow);
         while (longmask) {
@@ -168,15 +169,87 @@ __device__ __forceinline__ void expand_row_warp(const Csr& A, const Csr& B, int 
     }
 }
 
-// Same enumeration by a whole thread block: warps take interleaved 32-entry batches of the row of A.
-template <bool WITH_VALUES, class F>
+// Same enumeration by a whole thread block, load-balanced over the PRODUCTS rather than over the rows of B
+// (one hub row of B with 10^4 entries next to a hundred short ones is the normal case on power-law inputs):
+// the block loads the extents of up to blockDim rows of B at once, prefix-sums their lengths in shared
+// memory, and warps then take 128-product tiles of the flattened product range.  A tile finds its first row of
+// B by one binary search; each lane walks forward from there.  Consecutive lanes read consecutive entries of
+// B wherever a row of B is longer than a few entries, so the loads stay coalesced.
+template <int MAXT>
+struct SegScratch {
+    int start[MAXT];
+    int prefix[MAXT + 1];
+    double av[MAXT];
+    int red[33];
+};
+
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// `hook` runs once, after the first batch of extent loads has been issued and before their values are
+// consumed: independent work placed there (e.g. streaming zeros to the output row) overlaps the gather latency.
+template <bool WITH_VALUES, int MAXT, class F, class H = NoHook>
 __device__ __forceinline__ void expand_row_block(const Csr& A, const Csr& B, int a_begin, int a_end,
-                                                 int col_lo, int col_hi, bool windowed, bool b_sorted, F&& f) {
-    const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int base = a_begin + warp * 32; base < a_end; base += nwarp * 32) {
-        const int end = min(base + 32, a_end);
-        expand_row_warp<WITH_VALUES>(A, B, base, end, col_lo, col_hi, windowed, b_sorted, f);
+                                                 int col_lo, int col_hi, bool windowed, bool b_sorted,
+                                                 SegScratch<MAXT>& sc, F&& f, H&& hook = NoHook()) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+    const bool filter = windowed;
+    constexpr int U = 4, TILE = 32 * U;
+    bool first = true;
+    for (int base = a_begin; base < a_end; base += nt) {
+        const int p = base + tid;
+        int s = 0, len = 0;
+        double av = 0.0;
+        int j = -1;
+        if (p < a_end) {
+            j = __ldg(A.idx + p);
+            if (WITH_VALUES) av = __ldg(A.val + p);
+        }
+        int e = 0;
+        if (j >= 0) {
+            s = __ldg(B.ptr + j);
+            e = __ldg(B.ptr + j + 1);
+        }
+        if (first) { hook(); first = false; }
+        if (j >= 0) {
+            if (windowed && b_sorted && e - s > kClipMin) {
+                if (__ldg(B.idx + s) < col_lo) s = lower_bound(B.idx, s, e, col_lo);
+                if (e > s && __ldg(B.idx + e - 1) >= col_hi) e = lower_bound(B.idx, s, e, col_hi);
+            }
+            len = e - s;
+        }
+        int total;
+        const int ex = block_excl_scan<int>(len, sc.red, &total);
+        sc.start[tid] = s;
+        sc.prefix[tid] = ex;
+        if (WITH_VALUES) sc.av[tid] = av;
+        if (tid == nt - 1) sc.prefix[nt] = total;
+        __syncthreads();
+        const int nseg = min(nt, a_end - base);
+        for (int t0 = warp * TILE; t0 < total; t0 += nwarp * TILE) {
+            int lo = 0, hi = nseg;                 // prefix[lo] <= t0 < prefix[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (sc.prefix[mid] <= t0) lo = mid; else hi = mid;
+            }
+            int k = lo;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = t0 + u * 32 + lane;
+                if (t < total) {
+                    while (sc.prefix[k + 1] <= t) ++k;
+                    const int q = sc.start[k] + (t - sc.prefix[k]);
+                    const int c = __ldg(B.idx + q);
+                    if (!(filter && (c < col_lo || c >= col_hi)))
+                        f(c, WITH_VALUES ? sc.av[k] * __ldg(B.val + q) : 0.0);
+                }
+            }
+        }
+        __syncthreads();
     }
+    if (first) hook();
 }
 
 }  // namespace sb

@@ -15,7 +15,7 @@ enum { NUM_W64 = 0, NUM_W256, NUM_W1K, NUM_B4K, NUM_B16K, NUM_DENSE, NUM_BINS };
 
 constexpr int kWarpCap64 = 48, kWarpCap256 = 192, kWarpCap1K = 768;   // <= 75 % load of the warp tables
 constexpr int kBlockCap4K = 3072, kBlockCap16K = 12288;               // <= 75 % load of the block tables
-constexpr int kDenseWindow = 16384;                                   // doubles per dense accumulator window
+constexpr int kDenseWindow = 12288;                                   // doubles per dense accumulator window
 
 struct LaunchCtx {
     cudaStream_t stream;
@@ -72,8 +72,9 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
 cudaError_t sparse_kernels_configure();
 
 // ---- spgemm_dense.cu ----------------------------------------------------------------------------
+// mode: 0 = choose by products per output element, 1 = shared-memory tiles, 2 = zero-stream + global reductions
 cudaError_t launch_dense(const LaunchCtx& lc, const Csr& A, const Csr& B, const int32_t* d_b_sorted,
-                         bool upper_only, int row_begin, int nrows, double* d_c);
+                         bool upper_only, int row_begin, int nrows, double* d_c, int mode, double products_per_out);
 cudaError_t launch_mirror(const LaunchCtx& lc, double* d_c, int n);
 cudaError_t launch_symmetrize(const LaunchCtx& lc, double* d_c, int n);
 cudaError_t dense_kernels_configure();
@@ -81,7 +82,7 @@ cudaError_t dense_kernels_configure();
 // ---- triple.cu ----------------------------------------------------------------------------------
 cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht,
                           bool upper_only, int row_begin, int nrows, double* d_c,
-                          unsigned long long* d_counters /* [2]: P1, P2; may be null */);
+                          unsigned long long* d_counters /* [2]: P1, P2; may be null */, int mode);
 cudaError_t triple_kernels_configure();
 
 }  // namespace sb

@@ -16,7 +16,7 @@ namespace sb {
     } while (0)
 
 constexpr int kDenseThreads = 512;
-constexpr int kDenseTileMax = 12288;   // doubles per tile: 96 KB, two blocks per SM
+constexpr int kDenseTileMax = 12288;   // doubles per tile: 96 KB (+ 8 KB scratch), two blocks per SM
 
 // Write `count` doubles from shared `src` (or zeros when src == nullptr) to global `dst` with 16-byte stores
 // where alignment allows.
@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(kDenseThreads)
 k_dense_tiles(Csr A, Csr B, const int32_t* __restrict__ b_sorted_flag, int row_begin, int nrows, int tile_w,
               int ntiles, double* __restrict__ C) {
     extern __shared__ double acc[];
+    __shared__ SegScratch<kDenseThreads> s_seg;
     const int n = B.cols;
     const bool b_sorted = *b_sorted_flag != 0;
     for (int64_t item = blockIdx.x; item < (int64_t)nrows * ntiles; item += gridDim.x) {
@@ -57,11 +58,35 @@ k_dense_tiles(Csr A, Csr B, const int32_t* __restrict__ b_sorted_flag, int row_b
         }
         for (int x = threadIdx.x; x < t1 - t0; x += blockDim.x) acc[x] = 0.0;
         __syncthreads();
-        expand_row_block<true>(A, B, a_begin, a_end, lo, t1, UPPER || ntiles > 1, b_sorted,
+        expand_row_block<true>(A, B, a_begin, a_end, lo, t1, UPPER || ntiles > 1, b_sorted, s_seg,
                                [&](int c, double v) { atomicAdd(acc + (c - t0), v); });
         __syncthreads();
         stream_out(out, acc, t1 - t0);
         __syncthreads();
+    }
+}
+
+// Variant for outputs that are mostly zeros (few products per output element): a block owns a whole row of C.
+// It issues the gathers for the row of A, streams zeros over the row while they are in flight, and then adds
+// the products into the row with fire-and-forget float64 reductions that resolve in L2, where the freshly
+// written line still sits -- so DRAM sees each byte of C once, and no shared-memory tile is needed.
+constexpr int kDenseRedThreads = 256;
+
+template <bool UPPER>
+__global__ void __launch_bounds__(kDenseRedThreads)
+k_dense_rows_red(Csr A, Csr B, const int32_t* __restrict__ b_sorted_flag, int row_begin, int nrows,
+                 double* __restrict__ C) {
+    __shared__ SegScratch<kDenseRedThreads> s_seg;
+    const int n = B.cols;
+    const bool b_sorted = *b_sorted_flag != 0;
+    for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
+        const int i = row_begin + r;
+        const int a_begin = __ldg(A.ptr + i), a_end = __ldg(A.ptr + i + 1);
+        double* row = C + (size_t)r * n;
+        expand_row_block<true>(A, B, a_begin, a_end, UPPER ? i : 0, n, UPPER, b_sorted, s_seg,
+                               [&](int c, double v) { atomicAdd(row + c, v); },
+                               [&]() { stream_out(row, nullptr, n); });
+        // (the block-wide scan inside expand_row_block orders the zero stores before the reductions)
     }
 }
 
@@ -118,15 +143,26 @@ cudaError_t dense_kernels_configure() {
     e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
     g_dense_smem_optin = (size_t)optin;
-    e = cudaFuncSetAttribute(k_dense_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024);
+    e = cudaFuncSetAttribute(k_dense_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_dense_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024);
+    return cudaFuncSetAttribute(k_dense_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
 }
 
 cudaError_t launch_dense(const LaunchCtx& lc, const Csr& A, const Csr& B, const int32_t* d_b_sorted, bool upper_only,
-                         int row_begin, int nrows, double* d_c) {
+                         int row_begin, int nrows, double* d_c, int mode, double products_per_out) {
     const int n = B.cols;
     if (nrows <= 0 || n <= 0) return cudaSuccess;
+    if (mode == 0) mode = products_per_out < 0.5 ? 2 : 1;
+    if (mode == 2) {
+        int grid = lc.sm_count * 8;          // 8 resident blocks of 256 threads per SM
+        if (grid > nrows) grid = nrows;
+        if (upper_only)
+            k_dense_rows_red<true><<<grid, kDenseRedThreads, 0, lc.stream>>>(A, B, d_b_sorted, row_begin, nrows, d_c);
+        else
+            k_dense_rows_red<false><<<grid, kDenseRedThreads, 0, lc.stream>>>(A, B, d_b_sorted, row_begin, nrows, d_c);
+        SB_LAUNCH_CHECK(lc);
+        return cudaSuccess;
+    }
     // equal-width column tiles, each <= kDenseTileMax doubles and a multiple of 2 doubles wide
     int ntiles = (n + kDenseTileMax - 1) / kDenseTileMax;
     int tile_w = (n + ntiles - 1) / ntiles;
@@ -134,7 +170,7 @@ cudaError_t launch_dense(const LaunchCtx& lc, const Csr& A, const Csr& B, const 
     ntiles = (n + tile_w - 1) / tile_w;
     const size_t smem = (size_t)tile_w * sizeof(double);
     const int64_t items = (int64_t)nrows * ntiles;
-    int per_sm = (int)(g_dense_smem_optin / (smem + 1024));
+    int per_sm = (int)(g_dense_smem_optin / (smem + 10240));
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     // persistent-style grid: a multiple of the SM count, several waves so late rows balance

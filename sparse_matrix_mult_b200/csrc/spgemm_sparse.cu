@@ -111,6 +111,7 @@ k_symbolic_bitmap(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __
     extern __shared__ unsigned s_bits[];
     __shared__ int s_item;
     __shared__ int s_red[33];
+    __shared__ SegScratch<512> s_seg;
     const bool b_sorted = *b_sorted_flag != 0;
     const int n = B.cols;
     while (true) {
@@ -129,7 +130,7 @@ k_symbolic_bitmap(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __
             for (int t = threadIdx.x; t < words; t += blockDim.x) s_bits[t] = 0u;
             __syncthreads();
             const bool windowed = upper_only || window_bits < n;
-            expand_row_block<false>(A, B, a_begin, a_end, wl, wh, windowed, b_sorted, [&](int c, double) {
+            expand_row_block<false>(A, B, a_begin, a_end, wl, wh, windowed, b_sorted, s_seg, [&](int c, double) {
                 const int o = c - w0;
                 const unsigned m = 1u << (o & 31);
                 if (!(*((volatile unsigned*)(s_bits + (o >> 5))) & m)) atomicOr(s_bits + (o >> 5), m);
@@ -205,6 +206,7 @@ k_numeric_block(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __re
     int* keys = reinterpret_cast<int*>(s_dyn + slots);
     __shared__ int s_item;
     __shared__ int s_red[33];
+    __shared__ SegScratch<1024> s_seg;
     const bool b_sorted = *b_sorted_flag != 0;
     while (true) {
         if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
@@ -216,7 +218,7 @@ k_numeric_block(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __re
         for (int t = threadIdx.x; t < slots; t += blockDim.x) { keys[t] = kEmpty; vals[t] = 0.0; }
         __syncthreads();
         expand_row_block<true>(A, B, __ldg(A.ptr + i), __ldg(A.ptr + i + 1), upper_only ? i : 0, B.cols,
-                               upper_only != 0, b_sorted,
+                               upper_only != 0, b_sorted, s_seg,
                                [&](int c, double v) { hash_accumulate(keys, vals, (unsigned)slots, c, v); });
         __syncthreads();
         // in-place compaction, one chunk of blockDim slots at a time
@@ -256,6 +258,7 @@ k_numeric_dense(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __re
     unsigned* bits = reinterpret_cast<unsigned*>(s_dyn + window);
     __shared__ int s_item;
     __shared__ int s_red[33];
+    __shared__ SegScratch<512> s_seg;
     const bool b_sorted = *b_sorted_flag != 0;
     const int n = B.cols;
     while (true) {
@@ -275,7 +278,7 @@ k_numeric_dense(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __re
             for (int t = threadIdx.x; t < words; t += blockDim.x) bits[t] = 0u;
             __syncthreads();
             const bool windowed = upper_only || window < n;
-            expand_row_block<true>(A, B, a_begin, a_end, wl, wh, windowed, b_sorted, [&](int c, double v) {
+            expand_row_block<true>(A, B, a_begin, a_end, wl, wh, windowed, b_sorted, s_seg, [&](int c, double v) {
                 const int o = c - w0;
                 atomicAdd(acc + o, v);
                 const unsigned m = 1u << (o & 31);
@@ -316,11 +319,11 @@ cudaError_t sparse_kernels_configure() {
     e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
     g_smem_optin = (size_t)optin;
-    e = cudaFuncSetAttribute(k_symbolic_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024);
+    e = cudaFuncSetAttribute(k_symbolic_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_numeric_block, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024);
+    e = cudaFuncSetAttribute(k_numeric_block, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_numeric_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024);
+    e = cudaFuncSetAttribute(k_numeric_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
     return e;
 }
 
@@ -356,14 +359,14 @@ cudaError_t launch_symbolic(const LaunchCtx& lc, const SparseJob& job, const int
     }
     if (h_counts[SYM_BITMAP]) {
         // window = all columns when they fit the per-block shared memory, else the largest multiple of 32 bits
-        const size_t max_bits = (g_smem_optin - 2048) * 8;
+        const size_t max_bits = (g_smem_optin - 20480) * 8;
         size_t window_bits = (size_t)job.B.cols;
         if (window_bits > max_bits) window_bits = max_bits & ~(size_t)1023;
         if (window_bits < 32) window_bits = 32;
         window_bits = (window_bits + 31) & ~(size_t)31;
         const size_t smem = window_bits / 8;
         // several blocks per SM when the bitmap is small
-        int per_sm = (int)((g_smem_optin) / (smem + 1024));
+        int per_sm = (int)((g_smem_optin) / (smem + 10240));
         if (per_sm > 4) per_sm = 4;
         if (per_sm < 1) per_sm = 1;
         cudaError_t e = cudaMemsetAsync(d_work_counter, 0, sizeof(int32_t), lc.stream);
@@ -425,7 +428,7 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
         int window = kDenseWindow;
         if (job.B.cols < window) window = (job.B.cols + 31) & ~31;
         const size_t smem = (size_t)window * 8 + (size_t)window / 8 + 16;
-        int per_sm = (int)(g_smem_optin / (smem + 1024));
+        int per_sm = (int)(g_smem_optin / (smem + 10240));
         if (per_sm > 3) per_sm = 3;
         if (per_sm < 1) per_sm = 1;
         k_numeric_dense<<<grid_for(h_counts[NUM_DENSE], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(

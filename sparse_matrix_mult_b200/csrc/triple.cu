@@ -39,12 +39,26 @@ __device__ __forceinline__ void triple_stream_out(double* __restrict__ dst, cons
 }
 
 // counters[0] += expansion products (P1), counters[1] += scatter-adds performed (P2)
+__device__ __forceinline__ void triple_flush_counters(unsigned long long p1, unsigned long long p2,
+                                                      unsigned long long* s_cnt, unsigned long long* counters) {
+    if (!counters) return;
+    p1 = warp_sum(p1);
+    p2 = warp_sum(p2);
+    if (lane_id() == 0) {
+        if (p1) atomicAdd(&s_cnt[0], p1);
+        if (p2) atomicAdd(&s_cnt[1], p2);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 && s_cnt[threadIdx.x]) atomicAdd(counters + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
 template <bool UPPER>
 __global__ void __launch_bounds__(kTripleThreads)
 k_triple_tiles(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, int tile_w, int ntiles, double* __restrict__ C,
                unsigned long long* __restrict__ counters) {
     extern __shared__ double acc[];
     __shared__ unsigned long long s_cnt[2];
+    __shared__ SegScratch<kTripleThreads> s_seg;
     const int n = H.rows;
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -63,7 +77,7 @@ k_triple_tiles(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, int tile_w, int n
         }
         for (int x = threadIdx.x; x < t1 - t0; x += blockDim.x) acc[x] = 0.0;
         __syncthreads();
-        expand_row_block<true>(H, Q, h_begin, h_end, 0, 0, false, false, [&](int c, double w) {
+        expand_row_block<true>(H, Q, h_begin, h_end, 0, 0, false, false, s_seg, [&](int c, double w) {
             if (t == first_t) ++p1;                 // count the expansion once per row, not per tile
             const int s = __ldg(Ht.ptr + c), e = __ldg(Ht.ptr + c + 1);
             for (int q = s; q < e; ++q) {
@@ -78,16 +92,43 @@ k_triple_tiles(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, int tile_w, int n
         triple_stream_out(out, acc, t1 - t0);
         __syncthreads();
     }
-    if (counters) {
-        p1 = warp_sum(p1);
-        p2 = warp_sum(p2);
-        if (lane_id() == 0) {
-            if (p1) atomicAdd(&s_cnt[0], p1);
-            if (p2) atomicAdd(&s_cnt[1], p2);
-        }
-        __syncthreads();
-        if (threadIdx.x < 2 && s_cnt[threadIdx.x]) atomicAdd(counters + threadIdx.x, s_cnt[threadIdx.x]);
+    triple_flush_counters(p1, p2, s_cnt, counters);
+}
+
+// Variant without a shared-memory tile: the block owns a whole row of C, streams zeros over it while the
+// gathers of H[i,:] are in flight, then adds every contribution with a float64 reduction that resolves in L2
+// (native RED.ADD.F64 -- the shared-memory path needs a compare-and-swap loop per add).
+constexpr int kTripleRedThreads = 256;
+
+template <bool UPPER>
+__global__ void __launch_bounds__(kTripleRedThreads)
+k_triple_rows_red(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, double* __restrict__ C,
+                  unsigned long long* __restrict__ counters) {
+    __shared__ unsigned long long s_cnt[2];
+    __shared__ SegScratch<kTripleRedThreads> s_seg;
+    const int n = H.rows;
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long p1 = 0, p2 = 0;
+    for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
+        const int i = row_begin + r;
+        const int lo = UPPER ? i : 0;
+        double* row = C + (size_t)r * n;
+        expand_row_block<true>(H, Q, __ldg(H.ptr + i), __ldg(H.ptr + i + 1), 0, 0, false, false, s_seg,
+                               [&](int c, double w) {
+                                   ++p1;
+                                   const int s = __ldg(Ht.ptr + c), e = __ldg(Ht.ptr + c + 1);
+                                   for (int q = s; q < e; ++q) {
+                                       const int k = __ldg(Ht.idx + q);
+                                       if (k >= lo) {
+                                           atomicAdd(row + k, w * __ldg(Ht.val + q));
+                                           ++p2;
+                                       }
+                                   }
+                               },
+                               [&]() { triple_stream_out(row, nullptr, n); });
     }
+    triple_flush_counters(p1, p2, s_cnt, counters);
 }
 
 static size_t g_triple_smem_optin = 0;
@@ -99,22 +140,33 @@ cudaError_t triple_kernels_configure() {
     e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
     g_triple_smem_optin = (size_t)optin;
-    e = cudaFuncSetAttribute(k_triple_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024);
+    e = cudaFuncSetAttribute(k_triple_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_triple_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024);
+    return cudaFuncSetAttribute(k_triple_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
 }
 
 cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool upper_only,
-                          int row_begin, int nrows, double* d_c, unsigned long long* d_counters) {
+                          int row_begin, int nrows, double* d_c, unsigned long long* d_counters, int mode) {
     const int n = H.rows;
     if (nrows <= 0 || n <= 0) return cudaSuccess;
+    if (mode == 0) mode = 2;
+    if (mode == 2) {
+        int grid = lc.sm_count * 8;
+        if (grid > nrows) grid = nrows;
+        if (upper_only)
+            k_triple_rows_red<true><<<grid, kTripleRedThreads, 0, lc.stream>>>(H, Q, Ht, row_begin, nrows, d_c, d_counters);
+        else
+            k_triple_rows_red<false><<<grid, kTripleRedThreads, 0, lc.stream>>>(H, Q, Ht, row_begin, nrows, d_c, d_counters);
+        SB_LAUNCH_CHECK(lc);
+        return cudaSuccess;
+    }
     int ntiles = (n + kTripleTileMax - 1) / kTripleTileMax;
     int tile_w = (n + ntiles - 1) / ntiles;
     tile_w = (tile_w + 1) & ~1;
     ntiles = (n + tile_w - 1) / tile_w;
     const size_t smem = (size_t)tile_w * sizeof(double);
     const int64_t items = (int64_t)nrows * ntiles;
-    int per_sm = (int)(g_triple_smem_optin / (smem + 1024));
+    int per_sm = (int)(g_triple_smem_optin / (smem + 10240));
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)lc.sm_count * per_sm * 8;
