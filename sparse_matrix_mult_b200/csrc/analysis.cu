@@ -184,7 +184,7 @@ cudaError_t launch_scan_i32(const LaunchCtx& lc, const int32_t* in, int32_t* out
 // ---------------------------------------------------------------------------------------------------
 // Numeric binning by exact row nnz (one thread per row, block-aggregated list append).
 __global__ void __launch_bounds__(256)
-k_bin_by_nnz(const int32_t* __restrict__ nnz, int nrows, int single_window, int32_t* __restrict__ lists,
+k_bin_by_nnz(const int32_t* __restrict__ nnz, int nrows, int32_t* __restrict__ lists,
              int32_t* __restrict__ cursor) {
     __shared__ int s_cnt[NUM_BINS], s_base[NUM_BINS];
     if (threadIdx.x < NUM_BINS) s_cnt[threadIdx.x] = 0;
@@ -197,10 +197,7 @@ k_bin_by_nnz(const int32_t* __restrict__ nnz, int nrows, int single_window, int3
             if (c <= kWarpCap64) bin = NUM_W64;
             else if (c <= kWarpCap256) bin = NUM_W256;
             else if (c <= kWarpCap1K) bin = NUM_W1K;
-            else if (single_window) bin = NUM_DENSE;
-            else if (c <= kBlockCap4K) bin = NUM_B4K;
-            else if (c <= kBlockCap16K) bin = NUM_B16K;
-            else bin = NUM_DENSE;
+            else bin = NUM_RANK;
         }
     }
     int local = 0;
@@ -214,10 +211,10 @@ k_bin_by_nnz(const int32_t* __restrict__ nnz, int nrows, int single_window, int3
     if (bin >= 0) lists[(size_t)bin * nrows + s_base[bin] + local] = r;
 }
 
-cudaError_t launch_bin_by_nnz(const LaunchCtx& lc, const int32_t* d_nnz, int nrows, bool single_window,
-                              int32_t* d_lists, int32_t* d_cursor) {
+cudaError_t launch_bin_by_nnz(const LaunchCtx& lc, const int32_t* d_nnz, int nrows, int32_t* d_lists,
+                              int32_t* d_cursor) {
     if (nrows <= 0) return cudaSuccess;
-    k_bin_by_nnz<<<(nrows + 255) / 256, 256, 0, lc.stream>>>(d_nnz, nrows, single_window ? 1 : 0, d_lists, d_cursor);
+    k_bin_by_nnz<<<(nrows + 255) / 256, 256, 0, lc.stream>>>(d_nnz, nrows, d_lists, d_cursor);
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
 }

@@ -267,7 +267,7 @@ int csr_impl(spgemm_b200_mat* a, spgemm_b200_mat* b, int upper_only, int r0, int
     e = launch_symbolic(lc, job, d_lists, sym_counts, d_nnz, d_work);
     if (e == cudaSuccess) e = launch_scan_i64(lc, d_nnz, res->d_ptr, m, scan_tmp);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_cursor, 0, 16 * sizeof(int32_t), g.stream);
-    if (e == cudaSuccess) e = launch_bin_by_nnz(lc, d_nnz, m, n <= kDenseWindow, d_lists, d_cursor);
+    if (e == cudaSuccess) e = launch_bin_by_nnz(lc, d_nnz, m, d_lists, d_cursor);
     if (e != cudaSuccess) return bail(fail(SPGEMM_B200_ERR_CUDA, "symbolic phase", e));
     mark(EV_SYMBOLIC);
     int64_t* h64 = reinterpret_cast<int64_t*>(h + 32);

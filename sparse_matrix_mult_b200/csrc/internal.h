@@ -11,11 +11,9 @@ namespace sb {
 // symbolic bins, by the row's upper bound u = min(P_i, columns left)
 enum { SYM_W64 = 0, SYM_W256, SYM_W1K, SYM_BITMAP, SYM_BINS };
 // numeric bins, by the row's exact nnz
-enum { NUM_W64 = 0, NUM_W256, NUM_W1K, NUM_B4K, NUM_B16K, NUM_DENSE, NUM_BINS };
+enum { NUM_W64 = 0, NUM_W256, NUM_W1K, NUM_RANK, NUM_BINS };
 
 constexpr int kWarpCap64 = 48, kWarpCap256 = 192, kWarpCap1K = 768;   // <= 75 % load of the warp tables
-constexpr int kBlockCap4K = 3072, kBlockCap16K = 12288;               // <= 75 % load of the block tables
-constexpr int kDenseWindow = 12288;                                   // doubles per dense accumulator window
 
 struct LaunchCtx {
     cudaStream_t stream;
@@ -42,9 +40,9 @@ cudaError_t launch_check_sorted(const LaunchCtx& lc, const Csr& X, int64_t nnz, 
 cudaError_t launch_scan_i64(const LaunchCtx& lc, const int32_t* in, int64_t* out, int n, int64_t* d_tmp);
 cudaError_t launch_scan_i32(const LaunchCtx& lc, const int32_t* in, int32_t* out, int n, int64_t* d_tmp);
 
-// numeric binning by exact nnz; single_window: every row beyond the warp bins goes to NUM_DENSE
-cudaError_t launch_bin_by_nnz(const LaunchCtx& lc, const int32_t* d_nnz, int nrows, bool single_window,
-                              int32_t* d_lists, int32_t* d_cursor);
+// numeric binning by exact nnz
+cudaError_t launch_bin_by_nnz(const LaunchCtx& lc, const int32_t* d_nnz, int nrows, int32_t* d_lists,
+                              int32_t* d_cursor);
 
 // CSR transpose: counts -> scan -> fill.  Rows of the transpose come out in arbitrary order.
 cudaError_t launch_transpose_count(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_counts);

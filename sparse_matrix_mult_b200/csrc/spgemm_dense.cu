@@ -81,12 +81,13 @@ k_dense_rows_red(Csr A, Csr B, const int32_t* __restrict__ b_sorted_flag, int ro
     const bool b_sorted = *b_sorted_flag != 0;
     for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
         const int i = row_begin + r;
-        const int a_begin = __ldg(A.ptr + i), a_end = __ldg(A.ptr + i + 1);
         double* row = C + (size_t)r * n;
-        expand_row_block<true>(A, B, a_begin, a_end, UPPER ? i : 0, n, UPPER, b_sorted, s_seg,
-                               [&](int c, double v) { atomicAdd(row + c, v); },
-                               [&]() { stream_out(row, nullptr, n); });
+        stream_out(row, nullptr, n);            // no dependence on any load: the stores drain while we gather
+        const int a_begin = __ldg(A.ptr + i), a_end = __ldg(A.ptr + i + 1);
+        if (a_begin == a_end) continue;
         // (the block-wide scan inside expand_row_block orders the zero stores before the reductions)
+        expand_row_block<true>(A, B, a_begin, a_end, UPPER ? i : 0, n, UPPER, b_sorted, s_seg,
+                               [&](int c, double v) { atomicAdd(row + c, v); });
     }
 }
 
@@ -154,8 +155,7 @@ cudaError_t launch_dense(const LaunchCtx& lc, const Csr& A, const Csr& B, const 
     if (nrows <= 0 || n <= 0) return cudaSuccess;
     if (mode == 0) mode = products_per_out < 0.5 ? 2 : 1;
     if (mode == 2) {
-        int grid = lc.sm_count * 8;          // 8 resident blocks of 256 threads per SM
-        if (grid > nrows) grid = nrows;
+        const int grid = nrows;              // one block per row: the hardware scheduler keeps every SM writing
         if (upper_only)
             k_dense_rows_red<true><<<grid, kDenseRedThreads, 0, lc.stream>>>(A, B, d_b_sorted, row_begin, nrows, d_c);
         else

@@ -4,10 +4,10 @@
 // (/root/reference/src/sparsework.cpp:56-129 and :201-280) and its serial stitch
 // (/root/reference/src/sparse_sparse_sparse.cpp:265-291).  Here every row of C is owned by one warp or one
 // thread block, chosen by the row's cost bin:
-//   warp bins   : open-addressing hash table in shared memory (64 / 256 / 1024 slots per warp)
-//   block bins  : hash table of 4096 / 16384 slots per block, then an in-place bitonic sort by column
-//   bitmap/dense: a column window of the row is kept as a dense accumulator (+ occupancy bitmap) in shared
-//                 memory; windows are visited in order, so columns come out sorted without a sort
+//   warp bins : open-addressing hash table in shared memory (64 / 256 / 1024 slots per warp), compacted and
+//               bitonic-sorted by column inside the warp
+//   block bin : occupancy bitmap of the row in shared memory; a popcount prefix over it gives every column its
+//               rank in the sorted row, so values are accumulated in place in C (no hash table, no sort)
 // Output rows are written at their final position (int64 offsets from the scan of the symbolic counts):
 // no stitch pass.  Entries whose value cancels to zero stay (they are structural in the reference too).
 #include "internal.h"
@@ -196,71 +196,30 @@ k_numeric_warp(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __res
     }
 }
 
-// Numeric, block per row, hash table of `slots` entries in dynamic shared memory.
-__global__ void __launch_bounds__(1024)
-k_numeric_block(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __restrict__ b_sorted_flag,
-                const int32_t* __restrict__ list, int count, int slots, const int64_t* __restrict__ c_ptr,
-                int32_t* __restrict__ c_idx, double* __restrict__ c_val, int32_t* __restrict__ work_counter) {
-    extern __shared__ double s_dyn[];
-    double* vals = s_dyn;
-    int* keys = reinterpret_cast<int*>(s_dyn + slots);
-    __shared__ int s_item;
-    __shared__ int s_red[33];
-    __shared__ SegScratch<1024> s_seg;
-    const bool b_sorted = *b_sorted_flag != 0;
-    while (true) {
-        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
-        __syncthreads();
-        const int item = s_item;
-        __syncthreads();
-        if (item >= count) break;
-        const int r = __ldg(list + item), i = row_begin + r;
-        for (int t = threadIdx.x; t < slots; t += blockDim.x) { keys[t] = kEmpty; vals[t] = 0.0; }
-        __syncthreads();
-        expand_row_block<true>(A, B, __ldg(A.ptr + i), __ldg(A.ptr + i + 1), upper_only ? i : 0, B.cols,
-                               upper_only != 0, b_sorted, s_seg,
-                               [&](int c, double v) { hash_accumulate(keys, vals, (unsigned)slots, c, v); });
-        __syncthreads();
-        // in-place compaction, one chunk of blockDim slots at a time
-        int fill = 0;
-        for (int base = 0; base < slots; base += blockDim.x) {
-            const int t = base + threadIdx.x;
-            const int k = t < slots ? keys[t] : kEmpty;
-            const double v = t < slots ? vals[t] : 0.0;
-            int tot;
-            const int ex = block_excl_scan<int>(k != kEmpty ? 1 : 0, s_red, &tot);   // syncs: all reads done
-            if (k != kEmpty) { keys[fill + ex] = k; vals[fill + ex] = v; }
-            fill += tot;
-            __syncthreads();
-        }
-        int n2 = 2;
-        while (n2 < fill) n2 <<= 1;
-        for (int t = fill + threadIdx.x; t < n2; t += blockDim.x) keys[t] = kKeyMax;
-        __syncthreads();
-        bitonic_sort_pairs<true>(keys, vals, n2, threadIdx.x, blockDim.x);
-        const int64_t off = __ldg(c_ptr + r);
-        for (int t = threadIdx.x; t < fill; t += blockDim.x) {
-            c_idx[off + t] = keys[t];
-            c_val[off + t] = vals[t];
-        }
-        __syncthreads();
-    }
-}
-
-// Numeric, block per row, dense accumulator windows of `window` columns in dynamic shared memory:
-//   acc[window] doubles, then bits[window/32] occupancy words.
+// Numeric, block per row, for every row beyond the warp bins ("rank" kernel).  No hash table and no sort:
+//   pass 1  marks the row's columns in an occupancy bitmap in shared memory (as the symbolic phase did);
+//   prefix  two-level popcount prefix over the bitmap: rank(c) = number of occupied columns < c, i.e. the
+//           position of column c in the sorted output row;
+//   emit    the sorted column indices are written straight from the bitmap, the row's values are zeroed;
+//   pass 2  every product is added into C.val[row_offset + rank(col)] with a float64 reduction that resolves in
+//           L2 (native RED.ADD.F64; the row's slice of C.val was just written, so it is L2 resident).
+// Shared memory per block: bits[W/32] u32 + wpre[W/32] u16 + gpre[W/1024] i32 for a window of W columns
+// (W = all columns when they fit: 1,048,576 columns need 196 KB).  Wider matrices take several windows.
 __global__ void __launch_bounds__(512)
-k_numeric_dense(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __restrict__ b_sorted_flag,
-                const int32_t* __restrict__ list, int count, int window, const int64_t* __restrict__ c_ptr,
-                int32_t* __restrict__ c_idx, double* __restrict__ c_val, int32_t* __restrict__ work_counter) {
-    extern __shared__ double s_dyn[];
-    double* acc = s_dyn;
-    unsigned* bits = reinterpret_cast<unsigned*>(s_dyn + window);
+k_numeric_rank(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __restrict__ b_sorted_flag,
+               const int32_t* __restrict__ list, int count, int window, const int64_t* __restrict__ c_ptr,
+               int32_t* __restrict__ c_idx, double* __restrict__ c_val, int32_t* __restrict__ work_counter) {
+    extern __shared__ unsigned s_dynu[];
+    const int max_words = window >> 5;
+    unsigned* bits = s_dynu;
+    int* gpre = reinterpret_cast<int*>(s_dynu + max_words);
+    unsigned short* wpre = reinterpret_cast<unsigned short*>(gpre + (max_words >> 5) + 1);
     __shared__ int s_item;
     __shared__ int s_red[33];
     __shared__ SegScratch<512> s_seg;
     const bool b_sorted = *b_sorted_flag != 0;
     const int n = B.cols;
+    const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     while (true) {
         if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
         __syncthreads();
@@ -271,37 +230,59 @@ k_numeric_dense(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __re
         const int a_begin = __ldg(A.ptr + i), a_end = __ldg(A.ptr + i + 1);
         const int lo = upper_only ? i : 0;
         int64_t out = __ldg(c_ptr + r);
+        const int64_t row_end = __ldg(c_ptr + r + 1);
+        // the row's values start at zero (stores are ordered before the reductions by the barriers below)
+        for (int64_t t = out + threadIdx.x; t < row_end; t += blockDim.x) c_val[t] = 0.0;
         for (int w0 = (lo / window) * window; w0 < n; w0 += window) {
             const int wl = max(w0, lo), wh = min(w0 + window, n);
-            const int span = wh - w0, words = (span + 31) >> 5;
-            for (int t = threadIdx.x; t < span; t += blockDim.x) acc[t] = 0.0;
-            for (int t = threadIdx.x; t < words; t += blockDim.x) bits[t] = 0u;
-            __syncthreads();
+            const int words = (wh - w0 + 31) >> 5, groups = (words + 31) >> 5;
             const bool windowed = upper_only || window < n;
-            expand_row_block<true>(A, B, a_begin, a_end, wl, wh, windowed, b_sorted, s_seg, [&](int c, double v) {
+            for (int t = threadIdx.x; t < groups * 32; t += blockDim.x) bits[t] = 0u;
+            __syncthreads();
+            // pass 1: occupancy
+            expand_row_block<false>(A, B, a_begin, a_end, wl, wh, windowed, b_sorted, s_seg, [&](int c, double) {
                 const int o = c - w0;
-                atomicAdd(acc + o, v);
                 const unsigned m = 1u << (o & 31);
                 if (!(*((volatile unsigned*)(bits + (o >> 5))) & m)) atomicOr(bits + (o >> 5), m);
             });
             __syncthreads();
-            // ordered compaction of the window: one occupancy word per thread per pass
-            for (int base = 0; base < words; base += blockDim.x) {
-                const int wi = base + threadIdx.x;
-                unsigned word = wi < words ? bits[wi] : 0u;
+            // prefix, level 1: inside each group of 32 words (one warp per group, one word per lane)
+            for (int g = warp; g < groups; g += nwarp) {
+                const int pc = __popc(bits[(g << 5) + lane]);
+                const int inc = warp_incl_scan(pc);
+                wpre[(g << 5) + lane] = (unsigned short)(inc - pc);
+                if (lane == 31) gpre[g] = inc;
+            }
+            __syncthreads();
+            // prefix, level 2: exclusive scan of the group totals
+            int carry = 0;
+            for (int base = 0; base < groups; base += blockDim.x) {
+                const int g = base + threadIdx.x;
+                const int v = g < groups ? gpre[g] : 0;
                 int tot;
-                const int ex = block_excl_scan<int>(__popc(word), s_red, &tot);
-                int64_t pos = out + ex;
+                const int ex = block_excl_scan<int>(v, s_red, &tot);
+                if (g < groups) gpre[g] = carry + ex;
+                carry += tot;
+            }
+            __syncthreads();
+            // emit the sorted column indices of this window
+            for (int w = threadIdx.x; w < words; w += blockDim.x) {
+                unsigned word = bits[w];
+                int64_t pos = out + gpre[w >> 5] + wpre[w];
                 while (word) {
                     const int b = __ffs(word) - 1;
                     word &= word - 1;
-                    const int o = (wi << 5) + b;
-                    c_idx[pos] = w0 + o;
-                    c_val[pos] = acc[o];
-                    ++pos;
+                    c_idx[pos++] = w0 + (w << 5) + b;
                 }
-                out += tot;
             }
+            // pass 2: values
+            double* vals = c_val + out;
+            expand_row_block<true>(A, B, a_begin, a_end, wl, wh, windowed, b_sorted, s_seg, [&](int c, double v) {
+                const int o = c - w0, w = o >> 5;
+                const int rank = gpre[w >> 5] + wpre[w] + __popc(bits[w] & ((1u << (o & 31)) - 1u));
+                atomicAdd(vals + rank, v);
+            });
+            out += carry;
             __syncthreads();
         }
     }
@@ -321,9 +302,7 @@ cudaError_t sparse_kernels_configure() {
     g_smem_optin = (size_t)optin;
     e = cudaFuncSetAttribute(k_symbolic_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_numeric_block, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_numeric_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
+    e = cudaFuncSetAttribute(k_numeric_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
     return e;
 }
 
@@ -405,35 +384,20 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
             c_idx, c_val);
         SB_LAUNCH_CHECK(lc);
     }
-    // d_work_counter has one int per dynamically scheduled kernel (3 used here)
-    cudaError_t e = cudaMemsetAsync(d_work_counter, 0, 4 * sizeof(int32_t), lc.stream);
-    if (e != cudaSuccess) return e;
-    if (h_counts[NUM_B4K]) {
-        const int slots = 4096;
-        const size_t smem = (size_t)slots * 12;
-        k_numeric_block<<<grid_for(h_counts[NUM_B4K], 1, lc.sm_count * 4), 256, smem, lc.stream>>>(
-            job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_B4K * stride, h_counts[NUM_B4K], slots,
-            c_ptr, c_idx, c_val, d_work_counter + 1);
-        SB_LAUNCH_CHECK(lc);
-    }
-    if (h_counts[NUM_B16K]) {
-        const int slots = 16384;
-        const size_t smem = (size_t)slots * 12;
-        k_numeric_block<<<grid_for(h_counts[NUM_B16K], 1, lc.sm_count), 1024, smem, lc.stream>>>(
-            job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_B16K * stride, h_counts[NUM_B16K], slots,
-            c_ptr, c_idx, c_val, d_work_counter + 2);
-        SB_LAUNCH_CHECK(lc);
-    }
-    if (h_counts[NUM_DENSE]) {
-        int window = kDenseWindow;
-        if (job.B.cols < window) window = (job.B.cols + 31) & ~31;
-        const size_t smem = (size_t)window * 8 + (size_t)window / 8 + 16;
+    if (h_counts[NUM_RANK]) {
+        cudaError_t e = cudaMemsetAsync(d_work_counter, 0, sizeof(int32_t), lc.stream);
+        if (e != cudaSuccess) return e;
+        // window: all columns (rounded up to 1024) when bitmap + prefixes fit, else 2^20 columns
+        int64_t window = ((int64_t)job.B.cols + 1023) & ~(int64_t)1023;
+        auto smem_for = [](int64_t w) { return (size_t)(w / 8 + w / 16 + (w / 1024 + 1) * 4 + 16); };
+        if (smem_for(window) > g_smem_optin - 20480) window = 1 << 20;
+        const size_t smem = smem_for(window);
         int per_sm = (int)(g_smem_optin / (smem + 10240));
-        if (per_sm > 3) per_sm = 3;
+        if (per_sm > 4) per_sm = 4;
         if (per_sm < 1) per_sm = 1;
-        k_numeric_dense<<<grid_for(h_counts[NUM_DENSE], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
-            job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_DENSE * stride, h_counts[NUM_DENSE], window,
-            c_ptr, c_idx, c_val, d_work_counter + 3);
+        k_numeric_rank<<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
+            job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_RANK * stride, h_counts[NUM_RANK],
+            (int)window, c_ptr, c_idx, c_val, d_work_counter);
         SB_LAUNCH_CHECK(lc);
     }
     return cudaSuccess;

@@ -114,6 +114,7 @@ k_triple_rows_red(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, double* __rest
         const int i = row_begin + r;
         const int lo = UPPER ? i : 0;
         double* row = C + (size_t)r * n;
+        triple_stream_out(row, nullptr, n);
         expand_row_block<true>(H, Q, __ldg(H.ptr + i), __ldg(H.ptr + i + 1), 0, 0, false, false, s_seg,
                                [&](int c, double w) {
                                    ++p1;
@@ -125,8 +126,7 @@ k_triple_rows_red(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, double* __rest
                                            ++p2;
                                        }
                                    }
-                               },
-                               [&]() { triple_stream_out(row, nullptr, n); });
+                               });
     }
     triple_flush_counters(p1, p2, s_cnt, counters);
 }
@@ -151,8 +151,7 @@ cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const
     if (nrows <= 0 || n <= 0) return cudaSuccess;
     if (mode == 0) mode = 2;
     if (mode == 2) {
-        int grid = lc.sm_count * 8;
-        if (grid > nrows) grid = nrows;
+        const int grid = nrows;
         if (upper_only)
             k_triple_rows_red<true><<<grid, kTripleRedThreads, 0, lc.stream>>>(H, Q, Ht, row_begin, nrows, d_c, d_counters);
         else
