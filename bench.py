@@ -302,7 +302,7 @@ def run_ours(args, w, name, info, flops, rank, world):
     for _ in range(n_warm):
         step_device()
     barrier()
-    kernel_ms, step_ms, launches, bytes_min = [], [], 0, 0
+    kernel_ms, step_ms, launches, bytes_min, last_stats = [], [], 0, 0, {}
     with ClockSampler(local) as clocks:
         for _ in range(args.steps):
             if small:
@@ -313,6 +313,7 @@ def run_ours(args, w, name, info, flops, rank, world):
             lib.spgemm_b200_timer_stop(ms_c)
             step_ms.append(ms_c.value)
             st = dev.last_stats()
+            last_stats = st
             kernel_ms.append(st["ms_numeric"])
             launches += st["launches"]
             bytes_min = st["bytes_min"]
@@ -338,20 +339,23 @@ def run_ours(args, w, name, info, flops, rank, world):
     elif world == 1:
         ap = pinned_csr(a)
         bp = ap if (b is a) else pinned_csr(b)
-        for _ in range(min(2, args.warmup)):
-            r = sparse_matrix_multiply(ap, bp, **kw)
-            del r
-        e2e_ms, d2h_bytes = [], 0
-        for _ in range(args.steps):
-            t0 = time.perf_counter()
-            r = sparse_matrix_multiply(ap, bp, **kw)
-            e2e_ms.append((time.perf_counter() - t0) * 1e3)
-            d2h_bytes = r.nbytes if isinstance(r, np.ndarray) else (r.data.nbytes + r.indices.nbytes + r.indptr.nbytes)
-            del r
-        e2e_t = float(np.mean(e2e_ms))
-        e2e = {"value": flops / (e2e_t * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_t,
-               "h2d_bytes_per_step": int(csr_bytes(a) + (0 if (b is a and kind == "sparse") else csr_bytes(b))),
-               "d2h_bytes_per_step": int(d2h_bytes), "timing": "host wall clock around sparse_matrix_multiply()"}
+        try:
+            for _ in range(min(2, args.warmup)):
+                r = sparse_matrix_multiply(ap, bp, **kw)
+                del r
+            e2e_ms, d2h_bytes = [], 0
+            for _ in range(args.steps):
+                t0 = time.perf_counter()
+                r = sparse_matrix_multiply(ap, bp, **kw)
+                e2e_ms.append((time.perf_counter() - t0) * 1e3)
+                d2h_bytes = r.nbytes if isinstance(r, np.ndarray) else (r.data.nbytes + r.indices.nbytes + r.indptr.nbytes)
+                del r
+            e2e_t = float(np.mean(e2e_ms))
+            e2e = {"value": flops / (e2e_t * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_t,
+                   "h2d_bytes_per_step": int(csr_bytes(a) + (0 if (b is a and kind == "sparse") else csr_bytes(b))),
+                   "d2h_bytes_per_step": int(d2h_bytes), "timing": "host wall clock around sparse_matrix_multiply()"}
+        except OverflowError as ex:       # nnz(C) >= 2^31 cannot be returned as a SciPy int32 CSR (BASELINE cfg4)
+            e2e = {"value": None, "unit": UNIT, "unavailable": str(ex)}
     else:
         from sparse_matrix_mult_b200 import distributed as sd
         e2e = sd.bench_e2e(args, w, flops, rank, world, csr_bytes)
@@ -372,6 +376,9 @@ def run_ours(args, w, name, info, flops, rank, world):
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic_for(name),
                          "algorithmic_bytes": int(bytes_min), "kernel_ms": k_ms, "peak_source": peak_src},
+            "phases_ms": {k: round(last_stats.get(k, 0.0), 4) for k in
+                          ("ms_analysis", "ms_symbolic", "ms_numeric", "ms_post")},
+            "nnz_c": int(last_stats.get("nnz_c", 0)),
             "clocks": clocks.summary()}
     # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------
     if world == 1 and not args.no_cpu:

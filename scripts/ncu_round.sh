@@ -16,9 +16,9 @@ cap() {  # workload kernel-regex skip name
       $B --workload $1 > gpurun_out/ncu_full_$4.log 2>&1
   echo "full capture $4 rc=$?"
 }
-cap cfg2 k_dense_tiles 3 dense_cfg2
-cap cfg3 k_triple_tiles 3 triple_cfg3
-cap cfg4r k_numeric_dense 3 numdense_cfg4r
-cap cfg4r k_numeric_block 6 numblock_cfg4r
+cap cfg2 k_dense_rows_red 3 dense_cfg2
+cap cfg3 k_triple_rows_red 3 triple_cfg3
+cap cfg4r k_numeric_rank 3 numrank_cfg4r
 cap cfg4r k_symbolic_bitmap 3 symbitmap_cfg4r
+cap cfg1 "k_numeric_warp<256" 3 numwarp256_cfg1
 ls -la gpurun_out

@@ -169,16 +169,23 @@ __device__ __forceinline__ void expand_row_warp(const Csr& A, const Csr& B, int 
     }
 }
 
-// Same enumeration by a whole thread block, load-balanced over the PRODUCTS rather than over the rows of B
-// (one hub row of B with 10^4 entries next to a hundred short ones is the normal case on power-law inputs):
-// the block loads the extents of up to blockDim rows of B at once, prefix-sums their lengths in shared
-// memory, and warps then take 128-product tiles of the flattened product range.  A tile finds its first row of
-// B by one binary search; each lane walks forward from there.  Consecutive lanes read consecutive entries of
-// B wherever a row of B is longer than a few entries, so the loads stay coalesced.
+// Same enumeration by a whole thread block, balanced for power-law inputs (one hub row of B with 10^4 entries
+// next to hundreds of rows with 1-8 entries is the normal case there).  The block loads the extents of up to
+// blockDim rows of B at once -- one per thread, so the dependent gathers A.idx -> B.ptr are all in flight
+// together -- and then
+//   * every thread walks its own row of B when that row is short (< kBlockLong entries): no look-up at all;
+//   * long rows are cut into slices of kSlice entries; slices are numbered by a block-wide prefix sum and
+//     taken by warps round-robin, lanes striding the slice, so the loads of B are coalesced and a hub row is
+//     shared by all warps of the block.
+// f(col, prod) may be called divergently; it must not contain warp- or block-synchronous operations.
+constexpr int kBlockLong = 16;
+constexpr int kSlice = 512;
+
 template <int MAXT>
 struct SegScratch {
     int start[MAXT];
-    int prefix[MAXT + 1];
+    int len[MAXT];
+    int prefix[MAXT + 1];      // exclusive prefix of the slice counts
     double av[MAXT];
     int red[33];
 };
@@ -188,15 +195,15 @@ struct NoHook {
 };
 
 // `hook` runs once, after the first batch of extent loads has been issued and before their values are
-// consumed: independent work placed there (e.g. streaming zeros to the output row) overlaps the gather latency.
+// consumed: independent work placed there overlaps the gather latency.
 template <bool WITH_VALUES, int MAXT, class F, class H = NoHook>
 __device__ __forceinline__ void expand_row_block(const Csr& A, const Csr& B, int a_begin, int a_end,
                                                  int col_lo, int col_hi, bool windowed, bool b_sorted,
-                                                 SegScratch<MAXT>& sc, F&& f, H&& hook = NoHook()) {
+                                                 SegScratch<MAXT>& sc, F&& f, H&& hook = NoHook(),
+                                                 int clip_min = kClipMin) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     const bool filter = windowed;
-    constexpr int U = 4, TILE = 32 * U;
     bool first = true;
     for (int base = a_begin; base < a_end; base += nt) {
         const int p = base + tid;
@@ -214,40 +221,63 @@ __device__ __forceinline__ void expand_row_block(const Csr& A, const Csr& B, int
         }
         if (first) { hook(); first = false; }
         if (j >= 0) {
-            if (windowed && b_sorted && e - s > kClipMin) {
+            if (windowed && b_sorted && e - s > clip_min) {
                 if (__ldg(B.idx + s) < col_lo) s = lower_bound(B.idx, s, e, col_lo);
                 if (e > s && __ldg(B.idx + e - 1) >= col_hi) e = lower_bound(B.idx, s, e, col_hi);
             }
             len = e - s;
         }
+        const int nslice = len >= kBlockLong ? (len + kSlice - 1) / kSlice : 0;
         int total;
-        const int ex = block_excl_scan<int>(len, sc.red, &total);
-        sc.start[tid] = s;
-        sc.prefix[tid] = ex;
-        if (WITH_VALUES) sc.av[tid] = av;
-        if (tid == nt - 1) sc.prefix[nt] = total;
-        __syncthreads();
-        const int nseg = min(nt, a_end - base);
-        for (int t0 = warp * TILE; t0 < total; t0 += nwarp * TILE) {
-            int lo = 0, hi = nseg;                 // prefix[lo] <= t0 < prefix[hi]
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (sc.prefix[mid] <= t0) lo = mid; else hi = mid;
-            }
-            int k = lo;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int t = t0 + u * 32 + lane;
-                if (t < total) {
-                    while (sc.prefix[k + 1] <= t) ++k;
-                    const int q = sc.start[k] + (t - sc.prefix[k]);
-                    const int c = __ldg(B.idx + q);
-                    if (!(filter && (c < col_lo || c >= col_hi)))
-                        f(c, WITH_VALUES ? sc.av[k] * __ldg(B.val + q) : 0.0);
-                }
+        const int ex = block_excl_scan<int>(nslice, sc.red, &total);
+        if (total) {                                   // block-uniform
+            sc.start[tid] = s;
+            sc.len[tid] = len;
+            sc.prefix[tid] = ex;
+            if (WITH_VALUES) sc.av[tid] = av;
+            if (tid == nt - 1) sc.prefix[nt] = total;
+        }
+        // short rows: each thread walks its own
+        if (len < kBlockLong) {
+            for (int q = s; q < s + len; ++q) {
+                const int c = __ldg(B.idx + q);
+                if (!(filter && (c < col_lo || c >= col_hi))) f(c, WITH_VALUES ? av * __ldg(B.val + q) : 0.0);
             }
         }
-        __syncthreads();
+        if (total) {
+            __syncthreads();
+            const int nseg = min(nt, a_end - base);
+            for (int item = warp; item < total; item += nwarp) {
+                int lo = 0, hi = nseg;                 // prefix[lo] <= item < prefix[hi]; prefix[nseg..nt] == total
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (sc.prefix[mid] <= item) lo = mid; else hi = mid;
+                }
+                const int off = (item - sc.prefix[lo]) * kSlice;
+                const int q0 = sc.start[lo] + off;
+                const int cnt = min(kSlice, sc.len[lo] - off);
+                const double a = WITH_VALUES ? sc.av[lo] : 0.0;
+                // four independent loads per lane in flight before the first use
+                const int32_t* bi = B.idx + q0;
+                const double* bv = B.val + q0;
+                for (int q = lane; q < cnt; q += 128) {
+                    int c[4];
+                    double v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) c[u] = (q + 32 * u < cnt) ? __ldg(bi + q + 32 * u) : -1;
+                    if (WITH_VALUES) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) v[u] = (q + 32 * u < cnt) ? __ldg(bv + q + 32 * u) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (c[u] >= 0 && !(filter && (c[u] < col_lo || c[u] >= col_hi)))
+                            f(c[u], WITH_VALUES ? a * v[u] : 0.0);
+                    }
+                }
+            }
+            __syncthreads();
+        }
     }
     if (first) hook();
 }

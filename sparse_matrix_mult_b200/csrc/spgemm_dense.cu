@@ -72,6 +72,19 @@ k_dense_tiles(Csr A, Csr B, const int32_t* __restrict__ b_sorted_flag, int row_b
 // written line still sits -- so DRAM sees each byte of C once, and no shared-memory tile is needed.
 constexpr int kDenseRedThreads = 256;
 
+// zeros with the default (write-back) cache policy: the lines must still be in L2 when the reductions arrive
+__device__ __forceinline__ void zero_row(double* __restrict__ dst, int count) {
+    if (count <= 0) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int head = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1);
+    if (head && tid == 0) dst[0] = 0.0;
+    const int pairs = (count - head) >> 1;
+    double2* d2 = reinterpret_cast<double2*>(dst + head);
+    for (int t = tid; t < pairs; t += nt) d2[t] = make_double2(0.0, 0.0);
+    const int tail = head + 2 * pairs;
+    if (tail < count && tid == nt - 1) dst[tail] = 0.0;
+}
+
 template <bool UPPER>
 __global__ void __launch_bounds__(kDenseRedThreads)
 k_dense_rows_red(Csr A, Csr B, const int32_t* __restrict__ b_sorted_flag, int row_begin, int nrows,
@@ -82,7 +95,7 @@ k_dense_rows_red(Csr A, Csr B, const int32_t* __restrict__ b_sorted_flag, int ro
     for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
         const int i = row_begin + r;
         double* row = C + (size_t)r * n;
-        stream_out(row, nullptr, n);            // no dependence on any load: the stores drain while we gather
+        zero_row(row, n);                       // no dependence on any load: the stores drain while we gather
         const int a_begin = __ldg(A.ptr + i), a_end = __ldg(A.ptr + i + 1);
         if (a_begin == a_end) continue;
         // (the block-wide scan inside expand_row_block orders the zero stores before the reductions)

@@ -10,6 +10,8 @@
 //               rank in the sorted row, so values are accumulated in place in C (no hash table, no sort)
 // Output rows are written at their final position (int64 offsets from the scan of the symbolic counts):
 // no stitch pass.  Entries whose value cancels to zero stay (they are structural in the reference too).
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace sb {
@@ -198,28 +200,30 @@ k_numeric_warp(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __res
 
 // Numeric, block per row, for every row beyond the warp bins ("rank" kernel).  No hash table and no sort:
 //   pass 1  marks the row's columns in an occupancy bitmap in shared memory (as the symbolic phase did);
-//   prefix  two-level popcount prefix over the bitmap: rank(c) = number of occupied columns < c, i.e. the
-//           position of column c in the sorted output row;
-//   emit    the sorted column indices are written straight from the bitmap, the row's values are zeroed;
-//   pass 2  every product is added into C.val[row_offset + rank(col)] with a float64 reduction that resolves in
-//           L2 (native RED.ADD.F64; the row's slice of C.val was just written, so it is L2 resident).
-// Shared memory per block: bits[W/32] u32 + wpre[W/32] u16 + gpre[W/1024] i32 for a window of W columns
-// (W = all columns when they fit: 1,048,576 columns need 196 KB).  Wider matrices take several windows.
+//   prefix  exclusive popcount prefix per bitmap word: rank(c) = number of occupied columns < c, i.e. the
+//           position of column c in the sorted output row ({bits, prefix} pairs: one 64-bit shared load);
+//   emit    the sorted column indices are written straight from the bitmap;
+//   pass 2  the row's values are accumulated BY RANK in a compact shared-memory array of `cap` doubles (shared
+//           float64 atomics sustain ~2.7x the rate of L2 reductions on B200, scripts/micro/atomic_bw.cu) and
+//           leave with coalesced stores.  Rows with more than `cap` entries take several rank windows; a rank
+//           window is a column range, so with sorted B each window reads only its own part of the rows of B.
+// Shared memory per block: table[W/32] of {bits, prefix} (W = column window, all columns when they fit) and
+// vals[cap].  Wider matrices take several column windows.
+template <bool SMEM_ACC>
 __global__ void __launch_bounds__(512)
 k_numeric_rank(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __restrict__ b_sorted_flag,
-               const int32_t* __restrict__ list, int count, int window, const int64_t* __restrict__ c_ptr,
+               const int32_t* __restrict__ list, int count, int window, int cap, const int64_t* __restrict__ c_ptr,
                int32_t* __restrict__ c_idx, double* __restrict__ c_val, int32_t* __restrict__ work_counter) {
-    extern __shared__ unsigned s_dynu[];
-    const int max_words = window >> 5;
-    unsigned* bits = s_dynu;
-    int* gpre = reinterpret_cast<int*>(s_dynu + max_words);
-    unsigned short* wpre = reinterpret_cast<unsigned short*>(gpre + (max_words >> 5) + 1);
+    extern __shared__ double s_dynd[];
+    double* vals = s_dynd;
+    uint2* table = reinterpret_cast<uint2*>(s_dynd + cap);       // .x = occupancy bits, .y = exclusive prefix
+    unsigned* table_u = reinterpret_cast<unsigned*>(table);
     __shared__ int s_item;
     __shared__ int s_red[33];
+    __shared__ int s_bound[2];
     __shared__ SegScratch<512> s_seg;
     const bool b_sorted = *b_sorted_flag != 0;
     const int n = B.cols;
-    const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     while (true) {
         if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
         __syncthreads();
@@ -230,60 +234,99 @@ k_numeric_rank(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __res
         const int a_begin = __ldg(A.ptr + i), a_end = __ldg(A.ptr + i + 1);
         const int lo = upper_only ? i : 0;
         int64_t out = __ldg(c_ptr + r);
-        const int64_t row_end = __ldg(c_ptr + r + 1);
-        // the row's values start at zero (stores are ordered before the reductions by the barriers below)
-        for (int64_t t = out + threadIdx.x; t < row_end; t += blockDim.x) c_val[t] = 0.0;
         for (int w0 = (lo / window) * window; w0 < n; w0 += window) {
             const int wl = max(w0, lo), wh = min(w0 + window, n);
-            const int words = (wh - w0 + 31) >> 5, groups = (words + 31) >> 5;
-            const bool windowed = upper_only || window < n;
-            for (int t = threadIdx.x; t < groups * 32; t += blockDim.x) bits[t] = 0u;
+            const int words = (wh - w0 + 31) >> 5;
+            const bool col_windowed = upper_only || window < n;
+            for (int t = threadIdx.x; t < words; t += blockDim.x) table[t] = make_uint2(0u, 0u);
             __syncthreads();
             // pass 1: occupancy
-            expand_row_block<false>(A, B, a_begin, a_end, wl, wh, windowed, b_sorted, s_seg, [&](int c, double) {
+            expand_row_block<false>(A, B, a_begin, a_end, wl, wh, col_windowed, b_sorted, s_seg, [&](int c, double) {
                 const int o = c - w0;
                 const unsigned m = 1u << (o & 31);
-                if (!(*((volatile unsigned*)(bits + (o >> 5))) & m)) atomicOr(bits + (o >> 5), m);
+                unsigned* wp = table_u + 2 * (o >> 5);
+                if (!(*((volatile unsigned*)wp) & m)) atomicOr(wp, m);
             });
             __syncthreads();
-            // prefix, level 1: inside each group of 32 words (one warp per group, one word per lane)
-            for (int g = warp; g < groups; g += nwarp) {
-                const int pc = __popc(bits[(g << 5) + lane]);
-                const int inc = warp_incl_scan(pc);
-                wpre[(g << 5) + lane] = (unsigned short)(inc - pc);
-                if (lane == 31) gpre[g] = inc;
-            }
-            __syncthreads();
-            // prefix, level 2: exclusive scan of the group totals
-            int carry = 0;
-            for (int base = 0; base < groups; base += blockDim.x) {
-                const int g = base + threadIdx.x;
-                const int v = g < groups ? gpre[g] : 0;
+            // exclusive popcount prefix over the words
+            int nnz_w = 0;
+            for (int base = 0; base < words; base += blockDim.x) {
+                const int w = base + threadIdx.x;
+                const int pc = w < words ? __popc(table[w].x) : 0;
                 int tot;
-                const int ex = block_excl_scan<int>(v, s_red, &tot);
-                if (g < groups) gpre[g] = carry + ex;
-                carry += tot;
+                const int ex = block_excl_scan<int>(pc, s_red, &tot);
+                if (w < words) table[w].y = (unsigned)(nnz_w + ex);
+                nnz_w += tot;
             }
             __syncthreads();
-            // emit the sorted column indices of this window
+            // emit the sorted column indices of this column window
             for (int w = threadIdx.x; w < words; w += blockDim.x) {
-                unsigned word = bits[w];
-                int64_t pos = out + gpre[w >> 5] + wpre[w];
+                const uint2 e = table[w];
+                unsigned word = e.x;
+                int64_t pos = out + e.y;
                 while (word) {
                     const int b = __ffs(word) - 1;
                     word &= word - 1;
                     c_idx[pos++] = w0 + (w << 5) + b;
                 }
             }
-            // pass 2: values
-            double* vals = c_val + out;
-            expand_row_block<true>(A, B, a_begin, a_end, wl, wh, windowed, b_sorted, s_seg, [&](int c, double v) {
-                const int o = c - w0, w = o >> 5;
-                const int rank = gpre[w >> 5] + wpre[w] + __popc(bits[w] & ((1u << (o & 31)) - 1u));
-                atomicAdd(vals + rank, v);
-            });
-            out += carry;
-            __syncthreads();
+            if (!SMEM_ACC) {
+                // pass 2, variant: accumulate straight into C.val with L2 reductions (no rank windows)
+                double* gv = c_val + out;
+                for (int t = threadIdx.x; t < nnz_w; t += blockDim.x) gv[t] = 0.0;
+                __syncthreads();
+                expand_row_block<true>(A, B, a_begin, a_end, wl, wh, col_windowed, b_sorted, s_seg,
+                                       [&](int c, double v) {
+                                           const int o = c - w0;
+                                           const uint2 e = table[o >> 5];
+                                           atomicAdd(gv + (int)e.y + __popc(e.x & ((1u << (o & 31)) - 1u)), v);
+                                       });
+                out += nnz_w;
+                __syncthreads();
+                continue;
+            }
+            // pass 2: values, one rank window of <= cap entries at a time
+            const int nwin = (nnz_w + cap - 1) / cap;
+            for (int k = 0; k < nwin; ++k) {
+                const int r0 = k * cap, r1 = min(nnz_w, r0 + cap);
+                if (nwin > 1) {
+                    // column bounds of the rank window: column of rank r0 / r1 (threads 0 and 32 search)
+                    if (threadIdx.x == 0 || threadIdx.x == 32) {
+                        const int target = threadIdx.x == 0 ? r0 : r1;
+                        int col;
+                        if (target >= nnz_w) col = wh;
+                        else {
+                            int a = 0, b = words;            // largest w with prefix[w] <= target
+                            while (b - a > 1) {
+                                const int mid = (a + b) >> 1;
+                                if ((int)table[mid].y <= target) a = mid; else b = mid;
+                            }
+                            unsigned word = table[a].x;
+                            for (int skip = target - (int)table[a].y; skip > 0; --skip) word &= word - 1;
+                            col = w0 + (a << 5) + __ffs(word) - 1;
+                        }
+                        s_bound[threadIdx.x == 0 ? 0 : 1] = col;
+                    }
+                    __syncthreads();
+                }
+                const int cl = nwin > 1 ? max(s_bound[0], wl) : wl;
+                const int ch = nwin > 1 ? s_bound[1] : wh;
+                for (int t = threadIdx.x; t < r1 - r0; t += blockDim.x) vals[t] = 0.0;
+                __syncthreads();
+                expand_row_block<true>(A, B, a_begin, a_end, cl, ch, col_windowed || nwin > 1, b_sorted, s_seg,
+                                       [&](int c, double v) {
+                                           const int o = c - w0;
+                                           const uint2 e = table[o >> 5];
+                                           const int rank = (int)e.y + __popc(e.x & ((1u << (o & 31)) - 1u)) - r0;
+                                           atomicAdd(vals + rank, v);
+                                       },
+                                       NoHook(), nwin > 2 ? 4 : kClipMin);
+                __syncthreads();
+                double* dst = c_val + out + r0;
+                for (int t = threadIdx.x; t < r1 - r0; t += blockDim.x) dst[t] = vals[t];
+                __syncthreads();
+            }
+            out += nnz_w;
         }
     }
 }
@@ -302,7 +345,9 @@ cudaError_t sparse_kernels_configure() {
     g_smem_optin = (size_t)optin;
     e = cudaFuncSetAttribute(k_symbolic_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_numeric_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
+    e = cudaFuncSetAttribute(k_numeric_rank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_numeric_rank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
     return e;
 }
 
@@ -387,17 +432,34 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
     if (h_counts[NUM_RANK]) {
         cudaError_t e = cudaMemsetAsync(d_work_counter, 0, sizeof(int32_t), lc.stream);
         if (e != cudaSuccess) return e;
-        // window: all columns (rounded up to 1024) when bitmap + prefixes fit, else 2^20 columns
-        int64_t window = ((int64_t)job.B.cols + 1023) & ~(int64_t)1023;
-        auto smem_for = [](int64_t w) { return (size_t)(w / 8 + w / 16 + (w / 1024 + 1) * 4 + 16); };
-        if (smem_for(window) > g_smem_optin - 20480) window = 1 << 20;
-        const size_t smem = smem_for(window);
-        int per_sm = (int)(g_smem_optin / (smem + 10240));
+        // column window: all columns when the {bits, prefix} table (8 B per 32 columns) leaves room for a useful
+        // value array, else 2^19 columns (128 KB table)
+        const size_t max_dyn = g_smem_optin - 20480;                     // what sparse_kernels_configure allows
+        const size_t two_per_sm = g_smem_optin / 2 - 11264;              // dynamic bytes that still fit 2 blocks/SM
+        int64_t window = ((int64_t)job.B.cols + 31) & ~(int64_t)31;
+        if ((size_t)(window / 4) + 4096 * 8 > max_dyn) window = 1 << 19;
+        const size_t table_bytes = (size_t)(window / 4);
+        const size_t avail = (table_bytes + 4096 * 8 <= two_per_sm ? two_per_sm : max_dyn) - table_bytes;
+        int cap = (int)(avail / 8);
+        if (cap > 12288) cap = 12288;
+        const char* env_cap = getenv("SPGEMM_B200_RANK_CAP");
+        if (env_cap && atoi(env_cap) > 0 && atoi(env_cap) < cap) cap = atoi(env_cap);
+        cap &= ~31;
+        const char* env_mode = getenv("SPGEMM_B200_RANK_MODE");
+        const bool smem_acc = env_mode && atoi(env_mode) == 1;      // default: L2 reductions (faster as measured)
+        if (!smem_acc) cap = 0;
+        const size_t smem = (size_t)cap * 8 + table_bytes;
+        int per_sm = (int)((g_smem_optin + 1024) / (smem + 10240));
         if (per_sm > 4) per_sm = 4;
         if (per_sm < 1) per_sm = 1;
-        k_numeric_rank<<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
-            job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_RANK * stride, h_counts[NUM_RANK],
-            (int)window, c_ptr, c_idx, c_val, d_work_counter);
+        if (smem_acc)
+            k_numeric_rank<true><<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
+                job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_RANK * stride, h_counts[NUM_RANK],
+                (int)window, cap, c_ptr, c_idx, c_val, d_work_counter);
+        else
+            k_numeric_rank<false><<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
+                job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_RANK * stride, h_counts[NUM_RANK],
+                (int)window, cap, c_ptr, c_idx, c_val, d_work_counter);
         SB_LAUNCH_CHECK(lc);
     }
     return cudaSuccess;
