@@ -193,6 +193,8 @@ SPGEMM_B200_API void *spgemm_b200_device_alloc(size_t bytes);
 SPGEMM_B200_API void  spgemm_b200_device_free(void *d_ptr);
 SPGEMM_B200_API int   spgemm_b200_copy_to_host(void *host_dst, const void *d_src, size_t bytes);
 SPGEMM_B200_API int   spgemm_b200_copy_to_device(void *d_dst, const void *host_src, size_t bytes);
+/* device -> device on the library stream, asynchronous */
+SPGEMM_B200_API int   spgemm_b200_copy_on_device(void *d_dst, const void *d_src, size_t bytes);
 
 /* Make the library launch on `stream` (a cudaStream_t; NULL restores the library's own stream). */
 SPGEMM_B200_API int spgemm_b200_set_stream(void *stream);

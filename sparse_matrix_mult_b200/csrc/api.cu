@@ -745,6 +745,14 @@ int spgemm_b200_copy_to_device(void* d_dst, const void* host_src, size_t bytes) 
     return SPGEMM_B200_OK;
 }
 
+int spgemm_b200_copy_on_device(void* d_dst, const void* d_src, size_t bytes) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (bytes && (!d_dst || !d_src)) return fail(SPGEMM_B200_ERR_ARG, "copy_on_device: null pointer");
+    if (bytes) CU(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, g.stream));
+    return SPGEMM_B200_OK;
+}
+
 // ---- stopwatch / L2 flush ------------------------------------------------------------------------------------
 static cudaEvent_t t_ev0 = nullptr, t_ev1 = nullptr;
 static void* g_flush_buf = nullptr;

@@ -24,6 +24,12 @@ def set_stream(stream_ptr):
     _check(matrix_ops.get_lib().spgemm_b200_set_stream(_vp(stream_ptr or 0)), "spgemm_b200_set_stream")
 
 
+def copy_on_device(dst_ptr, src_ptr, nbytes):
+    """Device-to-device copy on the library stream (asynchronous)."""
+    _check(matrix_ops.get_lib().spgemm_b200_copy_on_device(_vp(dst_ptr), _vp(src_ptr), int(nbytes)),
+           "spgemm_b200_copy_on_device")
+
+
 def synchronize():
     _check(matrix_ops.get_lib().spgemm_b200_synchronize(), "spgemm_b200_synchronize")
 

@@ -1,0 +1,239 @@
+"""Row-sharded multi-GPU driver: one process per GPU, torch.distributed for the plumbing.
+
+SURVEY.md 8(e): every output row depends on one row of A (or H) and all of B (Q, H^T), so the path shards by rows
+with one broadcast in and one gather out.  The reference's analogue is `limits` (src/workdivision.cpp:16-89), an
+even split by row COUNT across OpenMP threads; here the split is by the per-row cost from the flop-counting pass
+(spgemm_b200_row_costs / spgemm_b200_partition), which matters on power-law inputs and for the upper-triangle
+triple product whose rows get cheaper towards the bottom.
+
+    rank 0 holds the host operands
+      -> dist.broadcast of the CSR arrays (NCCL over NVLink on GPUs, gloo in the CPU tests)
+      -> every rank: partition (identical on all ranks), compute its row block with the CUDA library
+      -> gather of the row blocks to rank 0 (dense: contiguous slabs; sparse: variable-size indices/values)
+
+The compute callback is injected so that the host-side logic (partition, broadcast packing, gather offsets) is
+testable on CPU with the gloo backend and the oracle as the per-rank compute (tests/test_distributed_cpu.py).
+"""
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+
+
+# ------------------------------------------------------------------------------------------------------
+# partition (host mirror of spgemm_b200_partition, used where costs are already on the host)
+def partition_by_cost(costs, parts):
+    """Contiguous row bounds (len parts+1) so that every part carries ~sum(costs+1)/parts."""
+    c = np.asarray(costs, dtype=np.float64) + 1.0
+    total = c.sum()
+    cum = np.cumsum(c)
+    bounds = np.zeros(parts + 1, dtype=np.int64)
+    for p in range(1, parts):
+        bounds[p] = int(np.searchsorted(cum, total * p / parts, side="left")) + 1
+    bounds[parts] = len(c)
+    bounds = np.minimum(np.maximum.accumulate(bounds), len(c))
+    return bounds
+
+
+def host_row_costs(a, b, kind, upper_only):
+    """Per-row cost on the host (numpy): products of A rows against B; for the triple product
+    P1_i + P2_i * (n - i)/n, the same model as k_triple_costs (csrc/analysis.cu)."""
+    blen = np.diff(b.indptr).astype(np.int64)
+    rows = np.repeat(np.arange(a.shape[0]), np.diff(a.indptr))
+    p1 = np.bincount(rows, weights=blen[a.indices], minlength=a.shape[0]).astype(np.float64)
+    if kind != "triple":
+        return p1
+    ht_len = np.bincount(a.indices, minlength=a.shape[1]).astype(np.int64)      # nnz of rows of H^T
+    # sum over (i,j) in H of sum_{c in Q_j} nnz(H^T_c): cost of row j of Q first, then gather by H's columns
+    qcost = np.add.reduceat(ht_len[b.indices], b.indptr[:-1]) if b.nnz else np.zeros(b.shape[0])
+    qcost = np.where(np.diff(b.indptr) > 0, qcost, 0).astype(np.float64)
+    p2 = np.bincount(rows, weights=qcost[a.indices], minlength=a.shape[0])
+    if upper_only:
+        n = a.shape[0]
+        p2 = p2 * (n - np.arange(n)) / max(1, n)
+    return p1 + p2
+
+
+# ------------------------------------------------------------------------------------------------------
+# broadcast of a CSR matrix from rank 0
+def _bcast_array(x, dtype, n, device, src=0):
+    t = torch.empty(n, dtype=dtype, device=device)
+    if dist.get_rank() == src:
+        t.copy_(torch.from_numpy(np.ascontiguousarray(x)).to(dtype))
+    dist.broadcast(t, src=src)
+    return t
+
+
+def broadcast_csr(x, device):
+    """rank 0 passes a scipy CSR, the others None; returns (shape, indptr, indices, data) tensors on `device`."""
+    meta = torch.zeros(3, dtype=torch.int64, device=device)
+    if dist.get_rank() == 0:
+        meta[:] = torch.tensor([x.shape[0], x.shape[1], x.nnz], dtype=torch.int64)
+    dist.broadcast(meta, src=0)
+    rows, cols, nnz = (int(v) for v in meta.tolist())
+    src = x if dist.get_rank() == 0 else None
+    indptr = _bcast_array(src.indptr if src is not None else None, torch.int32, rows + 1, device)
+    indices = _bcast_array(src.indices if src is not None else None, torch.int32, nnz, device)
+    data = _bcast_array(src.data if src is not None else None, torch.float64, nnz, device)
+    return (rows, cols), indptr, indices, data
+
+
+def tensors_to_scipy(shape, indptr, indices, data):
+    m = sp.csr_matrix(shape)
+    m.indptr, m.indices, m.data = indptr.cpu().numpy(), indices.cpu().numpy(), data.cpu().numpy()
+    return m
+
+
+# ------------------------------------------------------------------------------------------------------
+# gathers to rank 0
+def gather_dense_rows(local, bounds, ncols, device):
+    """local: (rows_of_this_rank, ncols) float64 tensor on `device`.  Rank 0 returns the stacked matrix."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if rank == 0:
+        full = torch.empty((int(bounds[-1]), ncols), dtype=torch.float64, device=device)
+        full[int(bounds[0]):int(bounds[1])] = local
+        reqs = [dist.irecv(full[int(bounds[r]):int(bounds[r + 1])], src=r) for r in range(1, world)
+                if bounds[r + 1] > bounds[r]]
+        for q in reqs:
+            q.wait()
+        return full
+    if local.numel():
+        dist.send(local.contiguous(), dst=0)
+    return None
+
+
+def gather_csr_rows(local_indptr, local_indices, local_data, bounds, device):
+    """Every rank passes its block's LOCAL indptr (int64, starts at 0), indices, data.  Rank 0 returns the
+    stitched (indptr int64, indices int32, data float64) -- the parallel replacement of the reference's serial
+    stitch (src/sparse_sparse_sparse.cpp:265-291)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    nnz_local = torch.tensor([int(local_indices.numel())], dtype=torch.int64, device=device)
+    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(counts, nnz_local)
+    counts = [int(c.item()) for c in counts]
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    if rank == 0:
+        rows = int(bounds[-1])
+        indptr = torch.zeros(rows + 1, dtype=torch.int64, device=device)
+        indices = torch.empty(int(offs[-1]), dtype=torch.int32, device=device)
+        data = torch.empty(int(offs[-1]), dtype=torch.float64, device=device)
+        indptr[int(bounds[0]):int(bounds[1]) + 1] = local_indptr
+        indices[:counts[0]] = local_indices
+        data[:counts[0]] = local_data
+        for r in range(1, world):
+            r0, r1 = int(bounds[r]), int(bounds[r + 1])
+            if r1 > r0:
+                buf = torch.empty(r1 - r0 + 1, dtype=torch.int64, device=device)
+                dist.recv(buf, src=r)
+                indptr[r0 + 1:r1 + 1] = buf[1:] + int(offs[r])
+            if counts[r]:
+                dist.recv(indices[int(offs[r]):int(offs[r + 1])], src=r)
+                dist.recv(data[int(offs[r]):int(offs[r + 1])], src=r)
+        return indptr, indices, data
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    if r1 > r0:
+        dist.send(local_indptr.contiguous(), dst=0)
+    if counts[rank]:
+        dist.send(local_indices.contiguous(), dst=0)
+        dist.send(local_data.contiguous(), dst=0)
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------
+def multiply_sharded(matrix_a, matrix_b, kind, upper_only, device, compute_block):
+    """The whole sharded product.  rank 0 passes scipy CSR operands (others None).
+
+    kind          : "sparse" | "dense" | "triple"
+    compute_block : f(a_tensors, b_tensors, r0, r1) -> dense (r1-r0, ncols) float64 tensor on `device`, or for
+                    kind == "sparse" a tuple (indptr int64[r1-r0+1], indices int32, data float64) of tensors.
+                    a_tensors / b_tensors are (shape, indptr, indices, data).
+    Returns on rank 0 the full result (dense tensor, or (indptr, indices, data) tensors); None elsewhere.
+    """
+    world = dist.get_world_size()
+    a_t = broadcast_csr(matrix_a, device)
+    b_t = broadcast_csr(matrix_b, device)
+    # identical partition on every rank: cost pass on the broadcast operands (host numpy here; the GPU driver
+    # in bench.py uses spgemm_b200_row_costs on the resident matrices instead)
+    a_h = tensors_to_scipy(*a_t)
+    b_h = tensors_to_scipy(*b_t)
+    bounds = partition_by_cost(host_row_costs(a_h, b_h, kind, upper_only), world)
+    r0, r1 = int(bounds[dist.get_rank()]), int(bounds[dist.get_rank() + 1])
+    block = compute_block(a_t, b_t, r0, r1)
+    if kind == "sparse":
+        return gather_csr_rows(block[0], block[1], block[2], bounds, device)
+    ncols = a_t[0][0] if kind == "triple" else b_t[0][1]
+    return gather_dense_rows(block, bounds, ncols, device)
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU compute callback + the end-to-end leg of bench.py at N > 1
+def cuda_compute_block(kind, upper_only):
+    """compute_block for multiply_sharded that runs the CUDA library on this rank's GPU, borrowing the broadcast
+    tensors (no copies) and launching on torch's current stream so that NCCL and the kernels are ordered."""
+    from . import device as dev
+
+    def run(a_t, b_t, r0, r1):
+        dev.set_stream(torch.cuda.current_stream().cuda_stream)
+        (ash, ap, ai, av), (bsh, bp, bi, bv) = a_t, b_t
+        A = dev.DeviceMatrix.wrap(ash, int(ai.numel()), ap.data_ptr(), ai.data_ptr(), av.data_ptr(), keep=a_t)
+        B = dev.DeviceMatrix.wrap(bsh, int(bi.numel()), bp.data_ptr(), bi.data_ptr(), bv.data_ptr(), keep=b_t)
+        if kind == "dense":
+            out = torch.empty((r1 - r0, bsh[1]), dtype=torch.float64, device=ap.device)
+            dev.spgemm_dense(A, B, upper_only, r0, r1, out=out.data_ptr())
+            return out
+        if kind == "triple":
+            out = torch.empty((r1 - r0, ash[0]), dtype=torch.float64, device=ap.device)
+            dev.triple_product(A, B, None, upper_only, r0, r1, out=out.data_ptr())
+            return out
+        res = dev.spgemm_csr(A, B, upper_only, r0, r1)
+        p, i, v = res.device_ptrs()
+        nnz, rows = res.nnz, r1 - r0
+        # copy out of the library's pool into torch tensors (device to device) before the handle is freed
+        indptr = torch.empty(rows + 1, dtype=torch.int64, device=ap.device)
+        indices = torch.empty(nnz, dtype=torch.int32, device=ap.device)
+        data = torch.empty(nnz, dtype=torch.float64, device=ap.device)
+        for dst, src, nbytes in ((indptr, p, (rows + 1) * 8), (indices, i, nnz * 4), (data, v, nnz * 8)):
+            dev.copy_on_device(dst.data_ptr(), src, nbytes)
+        dev.synchronize()
+        res.free()
+        return indptr, indices, data
+
+    return run
+
+
+def bench_e2e(args, w, flops, rank, world, csr_bytes):
+    """e2e at N GPUs: rank 0 starts from HOST operands and ends with a HOST result; every step does
+    H2D on rank 0 (inside broadcast_csr) -> NCCL broadcast -> sharded compute -> gather to rank 0 -> D2H."""
+    import time
+    device = torch.device("cuda", torch.cuda.current_device())
+    kind = w["kind"]
+    upper = kind == "triple" or bool(w["kwargs"].get("symmetric"))
+    a = w["a"] if rank == 0 else None
+    b = w["b"] if rank == 0 else None
+    fn = cuda_compute_block(kind, upper)
+    times, d2h = [], 0
+    for it in range(2 + args.steps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = multiply_sharded(a, b, kind, upper, device, fn)
+        if rank == 0:
+            if kind == "sparse":
+                host = [t.cpu() for t in out]
+                d2h = sum(t.numel() * t.element_size() for t in host)
+            else:
+                host = out.cpu()
+                d2h = host.numel() * 8
+        torch.cuda.synchronize()
+        dist.barrier()
+        if it >= 2:
+            times.append(time.perf_counter() - t0)
+        del out
+    t = torch.tensor([float(np.mean(times))], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    if rank != 0:
+        return None
+    return {"value": flops / sec / 1e9, "unit": "GFLOP/s", "ms_per_step": sec * 1e3,
+            "h2d_bytes_per_step": int(csr_bytes(w["a"]) + csr_bytes(w["b"])), "d2h_bytes_per_step": int(d2h),
+            "timing": "host wall clock on rank 0 incl. H2D, NCCL broadcast, sharded kernels, gather to rank 0, D2H"}

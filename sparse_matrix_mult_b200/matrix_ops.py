@@ -110,6 +110,7 @@ class MatrixOpsLibrary:
         L.spgemm_b200_device_free.restype = None
         L.spgemm_b200_copy_to_host.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.spgemm_b200_copy_to_device.argtypes = [_vp, _vp, ctypes.c_size_t]
+        L.spgemm_b200_copy_on_device.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.spgemm_b200_set_stream.argtypes = [_vp]
         L.spgemm_b200_timer_stop.argtypes = [ctypes.POINTER(ctypes.c_double)]
 
