@@ -360,12 +360,16 @@ def run_ours(args, w, name, info, flops, rank, world):
         from sparse_matrix_mult_b200 import distributed as sd
         e2e = sd.bench_e2e(args, w, flops, rank, world, csr_bytes)
 
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peak()
     k_ms = float(np.mean(kernel_ms))
     achieved = (bytes_min / 1e9) / (k_ms * 1e-3) if k_ms > 0 else 0.0
-    dominant = {"dense": "k_dense_tiles", "sparse": "numeric phase (k_numeric_*)", "triple": "k_triple_tiles"}[kind]
+    dominant = {"dense": "k_dense_rows_red", "sparse": "numeric phase (k_numeric_rank + k_numeric_warp<*>)",
+                "triple": "k_triple_rows_red"}[kind]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -30,6 +30,12 @@ def copy_on_device(dst_ptr, src_ptr, nbytes):
            "spgemm_b200_copy_on_device")
 
 
+def copy_to_host(host_array, src_ptr):
+    """Device -> host ndarray on the library stream; returns when the copy is done."""
+    _check(matrix_ops.get_lib().spgemm_b200_copy_to_host(host_array.ctypes.data_as(_vp), _vp(src_ptr),
+                                                         host_array.nbytes), "spgemm_b200_copy_to_host")
+
+
 def synchronize():
     _check(matrix_ops.get_lib().spgemm_b200_synchronize(), "spgemm_b200_synchronize")
 

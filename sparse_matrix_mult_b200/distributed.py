@@ -92,13 +92,15 @@ def gather_dense_rows(local, bounds, ncols, device):
     if rank == 0:
         full = torch.empty((int(bounds[-1]), ncols), dtype=torch.float64, device=device)
         full[int(bounds[0]):int(bounds[1])] = local
-        reqs = [dist.irecv(full[int(bounds[r]):int(bounds[r + 1])], src=r) for r in range(1, world)
-                if bounds[r + 1] > bounds[r]]
-        for q in reqs:
-            q.wait()
+        ops = [dist.P2POp(dist.irecv, full[int(bounds[r]):int(bounds[r + 1])], r) for r in range(1, world)
+               if bounds[r + 1] > bounds[r]]
+        if ops:                                   # one grouped launch (ncclGroupStart/End), not serialized recvs
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
         return full
     if local.numel():
-        dist.send(local.contiguous(), dst=0)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, local.contiguous(), 0)]):
+            q.wait()
     return None
 
 
@@ -120,27 +122,42 @@ def gather_csr_rows(local_indptr, local_indices, local_data, bounds, device):
         indptr[int(bounds[0]):int(bounds[1]) + 1] = local_indptr
         indices[:counts[0]] = local_indices
         data[:counts[0]] = local_data
+        ops, ptr_bufs = [], {}
         for r in range(1, world):
             r0, r1 = int(bounds[r]), int(bounds[r + 1])
             if r1 > r0:
-                buf = torch.empty(r1 - r0 + 1, dtype=torch.int64, device=device)
-                dist.recv(buf, src=r)
-                indptr[r0 + 1:r1 + 1] = buf[1:] + int(offs[r])
+                ptr_bufs[r] = torch.empty(r1 - r0 + 1, dtype=torch.int64, device=device)
+                ops.append(dist.P2POp(dist.irecv, ptr_bufs[r], r))
             if counts[r]:
-                dist.recv(indices[int(offs[r]):int(offs[r + 1])], src=r)
-                dist.recv(data[int(offs[r]):int(offs[r + 1])], src=r)
+                ops.append(dist.P2POp(dist.irecv, indices[int(offs[r]):int(offs[r + 1])], r))
+                ops.append(dist.P2POp(dist.irecv, data[int(offs[r]):int(offs[r + 1])], r))
+        if ops:
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
+        for r, buf in ptr_bufs.items():
+            indptr[int(bounds[r]) + 1:int(bounds[r + 1]) + 1] = buf[1:] + int(offs[r])
         return indptr, indices, data
     r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    ops = []
     if r1 > r0:
-        dist.send(local_indptr.contiguous(), dst=0)
+        ops.append(dist.P2POp(dist.isend, local_indptr.contiguous(), 0))
     if counts[rank]:
-        dist.send(local_indices.contiguous(), dst=0)
-        dist.send(local_data.contiguous(), dst=0)
+        ops.append(dist.P2POp(dist.isend, local_indices.contiguous(), 0))
+        ops.append(dist.P2POp(dist.isend, local_data.contiguous(), 0))
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
     return None
 
 
 # ------------------------------------------------------------------------------------------------------
-def multiply_sharded(matrix_a, matrix_b, kind, upper_only, device, compute_block):
+def host_partition(a_t, b_t, kind, upper_only, world):
+    """Partition from the broadcast operands with numpy (CPU tests; the GPU path uses cuda_partition)."""
+    a_h, b_h = tensors_to_scipy(*a_t), tensors_to_scipy(*b_t)
+    return partition_by_cost(host_row_costs(a_h, b_h, kind, upper_only), world)
+
+
+def multiply_sharded(matrix_a, matrix_b, kind, upper_only, device, compute_block, partition=host_partition):
     """The whole sharded product.  rank 0 passes scipy CSR operands (others None).
 
     kind          : "sparse" | "dense" | "triple"
@@ -152,11 +169,8 @@ def multiply_sharded(matrix_a, matrix_b, kind, upper_only, device, compute_block
     world = dist.get_world_size()
     a_t = broadcast_csr(matrix_a, device)
     b_t = broadcast_csr(matrix_b, device)
-    # identical partition on every rank: cost pass on the broadcast operands (host numpy here; the GPU driver
-    # in bench.py uses spgemm_b200_row_costs on the resident matrices instead)
-    a_h = tensors_to_scipy(*a_t)
-    b_h = tensors_to_scipy(*b_t)
-    bounds = partition_by_cost(host_row_costs(a_h, b_h, kind, upper_only), world)
+    # identical partition on every rank: the cost pass runs on the broadcast operands (deterministic integers)
+    bounds = partition(a_t, b_t, kind, upper_only, world)
     r0, r1 = int(bounds[dist.get_rank()]), int(bounds[dist.get_rank() + 1])
     block = compute_block(a_t, b_t, r0, r1)
     if kind == "sparse":
@@ -175,8 +189,7 @@ def cuda_compute_block(kind, upper_only):
     def run(a_t, b_t, r0, r1):
         dev.set_stream(torch.cuda.current_stream().cuda_stream)
         (ash, ap, ai, av), (bsh, bp, bi, bv) = a_t, b_t
-        A = dev.DeviceMatrix.wrap(ash, int(ai.numel()), ap.data_ptr(), ai.data_ptr(), av.data_ptr(), keep=a_t)
-        B = dev.DeviceMatrix.wrap(bsh, int(bi.numel()), bp.data_ptr(), bi.data_ptr(), bv.data_ptr(), keep=b_t)
+        A, B = _wrap(dev, a_t), _wrap(dev, b_t)
         if kind == "dense":
             out = torch.empty((r1 - r0, bsh[1]), dtype=torch.float64, device=ap.device)
             dev.spgemm_dense(A, B, upper_only, r0, r1, out=out.data_ptr())
@@ -201,6 +214,27 @@ def cuda_compute_block(kind, upper_only):
     return run
 
 
+def _wrap(dev, t):
+    shape, p, i, v = t
+    return dev.DeviceMatrix.wrap(shape, int(i.numel()), p.data_ptr(), i.data_ptr(), v.data_ptr(), keep=t)
+
+
+def cuda_partition(a_t, b_t, kind, upper_only, world):
+    """Flop-balanced bounds from the GPU cost pass (spgemm_b200_row_costs + spgemm_b200_partition)."""
+    from . import device as dev
+    from .matrix_ops import matrix_ops
+    dev.set_stream(torch.cuda.current_stream().cuda_stream)
+    A, B = _wrap(dev, a_t), _wrap(dev, b_t)
+    if kind == "triple":
+        Ht = A.transpose()
+        costs, _ = dev.row_costs(A, Ht, B, upper_only)
+    else:
+        costs, _ = dev.row_costs(A, B, None, upper_only)
+    bounds = dev.partition_rows(costs, a_t[0][0], world)
+    matrix_ops.get_lib().spgemm_b200_device_free(costs)
+    return bounds.astype(np.int64)
+
+
 def bench_e2e(args, w, flops, rank, world, csr_bytes):
     """e2e at N GPUs: rank 0 starts from HOST operands and ends with a HOST result; every step does
     H2D on rank 0 (inside broadcast_csr) -> NCCL broadcast -> sharded compute -> gather to rank 0 -> D2H."""
@@ -210,20 +244,26 @@ def bench_e2e(args, w, flops, rank, world, csr_bytes):
     upper = kind == "triple" or bool(w["kwargs"].get("symmetric"))
     a = w["a"] if rank == 0 else None
     b = w["b"] if rank == 0 else None
+    from . import device as dev
+    from .matrix_ops import _result_array
     fn = cuda_compute_block(kind, upper)
     times, d2h = [], 0
     for it in range(2 + args.steps):
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        out = multiply_sharded(a, b, kind, upper, device, fn)
+        out = multiply_sharded(a, b, kind, upper, device, fn, partition=cuda_partition)
         if rank == 0:
-            if kind == "sparse":
-                host = [t.cpu() for t in out]
-                d2h = sum(t.numel() * t.element_size() for t in host)
-            else:
-                host = out.cpu()
-                d2h = host.numel() * 8
+            # device -> pinned host arrays from the library's cache (what the single-GPU API returns too)
+            outs = out if kind == "sparse" else (out,)
+            d2h, host = 0, []
+            for t in outs:
+                h = _result_array(tuple(t.shape), {torch.int64: np.int64, torch.int32: np.int32,
+                                                   torch.float64: np.float64}[t.dtype])
+                dev.copy_to_host(h, t.data_ptr())
+                host.append(h)
+                d2h += h.nbytes
+            del host
         torch.cuda.synchronize()
         dist.barrier()
         if it >= 2:
