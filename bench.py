@@ -228,7 +228,7 @@ def run_reference_arm(args, w, name, info):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -392,7 +392,19 @@ def run_ours(args, w, name, info, flops, rank, world):
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": cflops / dt / 1e9, "unit": UNIT, "cores": cores, "kind": ckind,
                                 "sample": desc, "seconds": dt}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def ctypes_double():
@@ -414,6 +426,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference" and rank != 0:
         return 0
+    # exactly ONE line on stdout: libraries (NCCL prints its version banner there) are sent to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
     from sparse_matrix_mult_b200 import synthetic
     w = synthetic.workload(args.workload)
