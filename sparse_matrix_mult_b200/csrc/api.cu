@@ -566,8 +566,9 @@ int spgemm_b200_dense_dev(const spgemm_b200_mat* a, const spgemm_b200_mat* b, in
     mark(EV_H2D);
     if ((rc = ensure_sorted_flag(const_cast<spgemm_b200_mat*>(b)))) return rc;
     mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
-    CU(launch_dense(lctx(), view(a), view(b), b->d_sorted, upper_only != 0, row_begin, row_end - row_begin, d_c,
-                    env_mode("SPGEMM_B200_DENSE_MODE"), products_per_out(a, b)));
+    cudaError_t de = launch_dense(lctx(), view(a), view(b), b->d_sorted, upper_only != 0, row_begin, row_end - row_begin,
+                                  d_c, env_mode("SPGEMM_B200_DENSE_MODE"), products_per_out(a, b));
+    if (de != cudaSuccess) return fail(SPGEMM_B200_ERR_CUDA, "dense kernel", de);
     mark(EV_NUMERIC); mark(EV_POST); mark(EV_D2H);
     g.stats.nnz_c = (int64_t)(row_end - row_begin) * b->cols;
     g.stats.bytes_min = csr_bytes(a->rows, a->nnz) + csr_bytes(b->rows, b->nnz) + 8 * g.stats.nnz_c;

@@ -70,7 +70,7 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
 cudaError_t sparse_kernels_configure();
 
 // ---- spgemm_dense.cu ----------------------------------------------------------------------------
-// mode: 0 = choose by products per output element, 1 = shared-memory tiles, 2 = zero-stream + global reductions
+// mode: 0 = choose by products per output element, 1 = shared-memory tiles, 2 = block per row with L2 reductions
 cudaError_t launch_dense(const LaunchCtx& lc, const Csr& A, const Csr& B, const int32_t* d_b_sorted,
                          bool upper_only, int row_begin, int nrows, double* d_c, int mode, double products_per_out);
 cudaError_t launch_mirror(const LaunchCtx& lc, double* d_c, int n);

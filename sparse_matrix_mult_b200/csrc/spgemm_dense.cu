@@ -4,6 +4,8 @@
 // callocs C and scatter-adds every product into it.  Here the zero fill and the scatter are one pass: a thread
 // block owns (row, column tile), builds the tile in shared memory and streams it out with 128-bit stores, so
 // every byte of C is written exactly once and never read.  Tiles that receive no product skip shared memory.
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace sb {
@@ -72,35 +74,47 @@ k_dense_tiles(Csr A, Csr B, const int32_t* __restrict__ b_sorted_flag, int row_b
 // written line still sits -- so DRAM sees each byte of C once, and no shared-memory tile is needed.
 constexpr int kDenseRedThreads = 256;
 
-// zeros with the default (write-back) cache policy: the lines must still be in L2 when the reductions arrive
-__device__ __forceinline__ void zero_row(double* __restrict__ dst, int count) {
-    if (count <= 0) return;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int head = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1);
-    if (head && tid == 0) dst[0] = 0.0;
-    const int pairs = (count - head) >> 1;
-    double2* d2 = reinterpret_cast<double2*>(dst + head);
-    for (int t = tid; t < pairs; t += nt) d2[t] = make_double2(0.0, 0.0);
-    const int tail = head + 2 * pairs;
-    if (tail < count && tid == nt - 1) dst[tail] = 0.0;
-}
+// The row's products are gathered FIRST, into a small shared-memory list; only then are the zeros streamed and
+// the staged products added.  Gathering first matters: loads issued after the 160 KB of zero stores queue behind
+// them in the SM's memory pipeline, and by the time the reductions were issued the freshly written lines had
+// left L2 (every reduction then cost a DRAM read-modify-write).  Rows with more products than the list holds
+// zero first and reduce directly.
+constexpr int kDenseStage = 1024;
 
 template <bool UPPER>
 __global__ void __launch_bounds__(kDenseRedThreads)
 k_dense_rows_red(Csr A, Csr B, const int32_t* __restrict__ b_sorted_flag, int row_begin, int nrows,
                  double* __restrict__ C) {
     __shared__ SegScratch<kDenseRedThreads> s_seg;
+    __shared__ double s_val[kDenseStage];
+    __shared__ int s_col[kDenseStage];
+    __shared__ int s_count;
     const int n = B.cols;
     const bool b_sorted = *b_sorted_flag != 0;
     for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
         const int i = row_begin + r;
         double* row = C + (size_t)r * n;
-        zero_row(row, n);                       // no dependence on any load: the stores drain while we gather
         const int a_begin = __ldg(A.ptr + i), a_end = __ldg(A.ptr + i + 1);
-        if (a_begin == a_end) continue;
-        // (the block-wide scan inside expand_row_block orders the zero stores before the reductions)
-        expand_row_block<true>(A, B, a_begin, a_end, UPPER ? i : 0, n, UPPER, b_sorted, s_seg,
-                               [&](int c, double v) { atomicAdd(row + c, v); });
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+        if (a_begin != a_end)
+            expand_row_block<true>(A, B, a_begin, a_end, UPPER ? i : 0, n, UPPER, b_sorted, s_seg,
+                                   [&](int c, double v) {
+                                       const int pos = atomicAdd(&s_count, 1);
+                                       if (pos < kDenseStage) { s_col[pos] = c; s_val[pos] = v; }
+                                   });
+        stream_out(row, nullptr, n);            // evict-first: keeps A and B resident in L2 under the write stream
+        __syncthreads();                        // zero stores ordered before the reductions; list complete
+        const int staged = s_count;
+        if (staged <= kDenseStage) {
+            for (int t = threadIdx.x; t < staged; t += blockDim.x)
+                atomicAdd(row + s_col[t], s_val[t]);
+        } else {
+            // too many products to stage: enumerate them again, reducing directly
+            expand_row_block<true>(A, B, a_begin, a_end, UPPER ? i : 0, n, UPPER, b_sorted, s_seg,
+                                   [&](int c, double v) { atomicAdd(row + c, v); });
+        }
+        __syncthreads();
     }
 }
 
