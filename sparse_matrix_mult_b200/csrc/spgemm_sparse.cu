@@ -106,14 +106,15 @@ k_symbolic_warp(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __re
 }
 
 // Symbolic, block per row, occupancy bitmap over column windows of `window_bits` columns.
-__global__ void __launch_bounds__(512)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
 k_symbolic_bitmap(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __restrict__ b_sorted_flag,
                   const int32_t* __restrict__ list, int count, int window_bits, int32_t* __restrict__ nnz,
                   int32_t* __restrict__ work_counter) {
     extern __shared__ unsigned s_bits[];
     __shared__ int s_item;
     __shared__ int s_red[33];
-    __shared__ SegScratch<512> s_seg;
+    __shared__ SegScratch<THREADS> s_seg;
     const bool b_sorted = *b_sorted_flag != 0;
     const int n = B.cols;
     while (true) {
@@ -200,28 +201,54 @@ k_numeric_warp(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __res
 
 // Numeric, block per row, for every row beyond the warp bins ("rank" kernel).  No hash table and no sort:
 //   pass 1  marks the row's columns in an occupancy bitmap in shared memory (as the symbolic phase did);
-//   prefix  exclusive popcount prefix per bitmap word: rank(c) = number of occupied columns < c, i.e. the
-//           position of column c in the sorted output row ({bits, prefix} pairs: one 64-bit shared load);
-//   emit    the sorted column indices are written straight from the bitmap;
-//   pass 2  the row's values are accumulated BY RANK in a compact shared-memory array of `cap` doubles (shared
-//           float64 atomics sustain ~2.7x the rate of L2 reductions on B200, scripts/micro/atomic_bw.cu) and
-//           leave with coalesced stores.  Rows with more than `cap` entries take several rank windows; a rank
-//           window is a column range, so with sorted B each window reads only its own part of the rows of B.
-// Shared memory per block: table[W/32] of {bits, prefix} (W = column window, all columns when they fit) and
-// vals[cap].  Wider matrices take several column windows.
-template <bool SMEM_ACC>
-__global__ void __launch_bounds__(512)
+//   prefix  exclusive popcount prefix over the bitmap: rank(c) = number of occupied columns < c, i.e. the
+//           position of column c in the sorted output row;
+//   emit    the sorted column indices are written straight from the bitmap, the row's values are zeroed;
+//   pass 2  every product is added into C.val[row_offset + rank(col)] with a float64 reduction that resolves in
+//           L2 (native RED.ADD.F64; the row's slice of C.val was just written, so it is L2 resident).
+// Two table layouts:
+//   COMPACT = false  {bits, prefix} pair per 32 columns (8 B): one 64-bit shared load per rank.  65,536 columns
+//                    need 16 KB, so several blocks share an SM.
+//   COMPACT = true   bits[W/32] plus one prefix per FOUR words (5 B per 32 columns): 1,048,576 columns fit one
+//                    160 KB table, one 1024-thread block per SM, a 128-bit shared load per rank.
+// Matrices wider than the table take several column windows.
+// (A variant that accumulated by rank in shared memory, in rank windows, measured slower than the L2 reductions
+//  on every config and was removed -- DESIGN.md section 7.)
+template <bool COMPACT>
+struct RankTable {
+    unsigned* bits;      // COMPACT: bits[words];            else: interleaved {bits, prefix}
+    unsigned* pre;       // COMPACT: prefix per 4 words;     else: unused
+    __device__ __forceinline__ unsigned* word_ptr(int w) const { return COMPACT ? bits + w : bits + 2 * w; }
+    __device__ __forceinline__ int rank(int o) const {
+        const int w = o >> 5;
+        const unsigned below = (1u << (o & 31)) - 1u;
+        if (!COMPACT) {
+            const uint2 e = reinterpret_cast<const uint2*>(bits)[w];
+            return (int)e.y + __popc(e.x & below);
+        }
+        const uint4 b = reinterpret_cast<const uint4*>(bits)[w >> 2];
+        const int k = w & 3;
+        const unsigned cur = k == 0 ? b.x : k == 1 ? b.y : k == 2 ? b.z : b.w;
+        int r = (int)pre[w >> 2] + __popc(cur & below);
+        if (k > 0) r += __popc(b.x);
+        if (k > 1) r += __popc(b.y);
+        if (k > 2) r += __popc(b.z);
+        return r;
+    }
+};
+
+template <bool COMPACT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 k_numeric_rank(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __restrict__ b_sorted_flag,
-               const int32_t* __restrict__ list, int count, int window, int cap, const int64_t* __restrict__ c_ptr,
+               const int32_t* __restrict__ list, int count, int window, const int64_t* __restrict__ c_ptr,
                int32_t* __restrict__ c_idx, double* __restrict__ c_val, int32_t* __restrict__ work_counter) {
-    extern __shared__ double s_dynd[];
-    double* vals = s_dynd;
-    uint2* table = reinterpret_cast<uint2*>(s_dynd + cap);       // .x = occupancy bits, .y = exclusive prefix
-    unsigned* table_u = reinterpret_cast<unsigned*>(table);
+    extern __shared__ unsigned s_dynu[];
+    RankTable<COMPACT> tab;
+    tab.bits = s_dynu;
+    tab.pre = s_dynu + (window >> 5);            // COMPACT only
     __shared__ int s_item;
     __shared__ int s_red[33];
-    __shared__ int s_bound[2];
-    __shared__ SegScratch<512> s_seg;
+    __shared__ SegScratch<THREADS> s_seg;
     const bool b_sorted = *b_sorted_flag != 0;
     const int n = B.cols;
     while (true) {
@@ -236,97 +263,63 @@ k_numeric_rank(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __res
         int64_t out = __ldg(c_ptr + r);
         for (int w0 = (lo / window) * window; w0 < n; w0 += window) {
             const int wl = max(w0, lo), wh = min(w0 + window, n);
-            const int words = (wh - w0 + 31) >> 5;
+            const int words = (((wh - w0 + 31) >> 5) + 3) & ~3;            // multiple of 4 (window is one of 128)
             const bool col_windowed = upper_only || window < n;
-            for (int t = threadIdx.x; t < words; t += blockDim.x) table[t] = make_uint2(0u, 0u);
+            if (COMPACT) for (int t = threadIdx.x; t < words; t += THREADS) tab.bits[t] = 0u;
+            else for (int t = threadIdx.x; t < words; t += THREADS) reinterpret_cast<uint2*>(tab.bits)[t] = make_uint2(0u, 0u);
             __syncthreads();
             // pass 1: occupancy
             expand_row_block<false>(A, B, a_begin, a_end, wl, wh, col_windowed, b_sorted, s_seg, [&](int c, double) {
                 const int o = c - w0;
                 const unsigned m = 1u << (o & 31);
-                unsigned* wp = table_u + 2 * (o >> 5);
+                unsigned* wp = tab.word_ptr(o >> 5);
                 if (!(*((volatile unsigned*)wp) & m)) atomicOr(wp, m);
             });
             __syncthreads();
-            // exclusive popcount prefix over the words
+            // exclusive popcount prefix (per word, or per group of four words)
+            const int units = COMPACT ? words >> 2 : words;
             int nnz_w = 0;
-            for (int base = 0; base < words; base += blockDim.x) {
-                const int w = base + threadIdx.x;
-                const int pc = w < words ? __popc(table[w].x) : 0;
+            for (int base = 0; base < units; base += THREADS) {
+                const int u = base + threadIdx.x;
+                int pc = 0;
+                if (u < units) {
+                    if (COMPACT) {
+                        const uint4 b = reinterpret_cast<const uint4*>(tab.bits)[u];
+                        pc = __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+                    } else {
+                        pc = __popc(tab.bits[2 * u]);
+                    }
+                }
                 int tot;
                 const int ex = block_excl_scan<int>(pc, s_red, &tot);
-                if (w < words) table[w].y = (unsigned)(nnz_w + ex);
+                if (u < units) {
+                    if (COMPACT) tab.pre[u] = (unsigned)(nnz_w + ex); else tab.bits[2 * u + 1] = (unsigned)(nnz_w + ex);
+                }
                 nnz_w += tot;
             }
             __syncthreads();
-            // emit the sorted column indices of this column window
-            for (int w = threadIdx.x; w < words; w += blockDim.x) {
-                const uint2 e = table[w];
-                unsigned word = e.x;
-                int64_t pos = out + e.y;
-                while (word) {
-                    const int b = __ffs(word) - 1;
-                    word &= word - 1;
-                    c_idx[pos++] = w0 + (w << 5) + b;
-                }
-            }
-            if (!SMEM_ACC) {
-                // pass 2, variant: accumulate straight into C.val with L2 reductions (no rank windows)
-                double* gv = c_val + out;
-                for (int t = threadIdx.x; t < nnz_w; t += blockDim.x) gv[t] = 0.0;
-                __syncthreads();
-                expand_row_block<true>(A, B, a_begin, a_end, wl, wh, col_windowed, b_sorted, s_seg,
-                                       [&](int c, double v) {
-                                           const int o = c - w0;
-                                           const uint2 e = table[o >> 5];
-                                           atomicAdd(gv + (int)e.y + __popc(e.x & ((1u << (o & 31)) - 1u)), v);
-                                       });
-                out += nnz_w;
-                __syncthreads();
-                continue;
-            }
-            // pass 2: values, one rank window of <= cap entries at a time
-            const int nwin = (nnz_w + cap - 1) / cap;
-            for (int k = 0; k < nwin; ++k) {
-                const int r0 = k * cap, r1 = min(nnz_w, r0 + cap);
-                if (nwin > 1) {
-                    // column bounds of the rank window: column of rank r0 / r1 (threads 0 and 32 search)
-                    if (threadIdx.x == 0 || threadIdx.x == 32) {
-                        const int target = threadIdx.x == 0 ? r0 : r1;
-                        int col;
-                        if (target >= nnz_w) col = wh;
-                        else {
-                            int a = 0, b = words;            // largest w with prefix[w] <= target
-                            while (b - a > 1) {
-                                const int mid = (a + b) >> 1;
-                                if ((int)table[mid].y <= target) a = mid; else b = mid;
-                            }
-                            unsigned word = table[a].x;
-                            for (int skip = target - (int)table[a].y; skip > 0; --skip) word &= word - 1;
-                            col = w0 + (a << 5) + __ffs(word) - 1;
-                        }
-                        s_bound[threadIdx.x == 0 ? 0 : 1] = col;
+            // emit the sorted column indices of this column window; zero the values they will accumulate into
+            for (int u = threadIdx.x; u < units; u += THREADS) {
+                int64_t pos = out + (COMPACT ? tab.pre[u] : tab.bits[2 * u + 1]);
+                const int nw = COMPACT ? 4 : 1;
+                for (int k = 0; k < nw; ++k) {
+                    const int w = COMPACT ? 4 * u + k : u;
+                    unsigned word = *tab.word_ptr(w);
+                    while (word) {
+                        const int b = __ffs(word) - 1;
+                        word &= word - 1;
+                        c_idx[pos++] = w0 + (w << 5) + b;
                     }
-                    __syncthreads();
                 }
-                const int cl = nwin > 1 ? max(s_bound[0], wl) : wl;
-                const int ch = nwin > 1 ? s_bound[1] : wh;
-                for (int t = threadIdx.x; t < r1 - r0; t += blockDim.x) vals[t] = 0.0;
-                __syncthreads();
-                expand_row_block<true>(A, B, a_begin, a_end, cl, ch, col_windowed || nwin > 1, b_sorted, s_seg,
-                                       [&](int c, double v) {
-                                           const int o = c - w0;
-                                           const uint2 e = table[o >> 5];
-                                           const int rank = (int)e.y + __popc(e.x & ((1u << (o & 31)) - 1u)) - r0;
-                                           atomicAdd(vals + rank, v);
-                                       },
-                                       NoHook(), nwin > 2 ? 4 : kClipMin);
-                __syncthreads();
-                double* dst = c_val + out + r0;
-                for (int t = threadIdx.x; t < r1 - r0; t += blockDim.x) dst[t] = vals[t];
-                __syncthreads();
             }
+            double* gv = c_val + out;
+            for (int t = threadIdx.x; t < nnz_w; t += THREADS) gv[t] = 0.0;
+            __syncthreads();
+            // pass 2: values
+            expand_row_block<true>(A, B, a_begin, a_end, wl, wh, col_windowed, b_sorted, s_seg,
+                                   [&](int c, double v) { atomicAdd(gv + tab.rank(c - w0), v); });
             out += nnz_w;
+            __syncthreads();
         }
     }
 }
@@ -343,11 +336,13 @@ cudaError_t sparse_kernels_configure() {
     e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
     g_smem_optin = (size_t)optin;
-    e = cudaFuncSetAttribute(k_symbolic_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
+    e = cudaFuncSetAttribute(k_symbolic_bitmap<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_numeric_rank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
+    e = cudaFuncSetAttribute(k_symbolic_bitmap<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 24576);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_numeric_rank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
+    e = cudaFuncSetAttribute(k_numeric_rank<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_numeric_rank<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 24576);
     return e;
 }
 
@@ -383,7 +378,7 @@ cudaError_t launch_symbolic(const LaunchCtx& lc, const SparseJob& job, const int
     }
     if (h_counts[SYM_BITMAP]) {
         // window = all columns when they fit the per-block shared memory, else the largest multiple of 32 bits
-        const size_t max_bits = (g_smem_optin - 20480) * 8;
+        const size_t max_bits = (g_smem_optin - 24576) * 8;
         size_t window_bits = (size_t)job.B.cols;
         if (window_bits > max_bits) window_bits = max_bits & ~(size_t)1023;
         if (window_bits < 32) window_bits = 32;
@@ -395,9 +390,14 @@ cudaError_t launch_symbolic(const LaunchCtx& lc, const SparseJob& job, const int
         if (per_sm < 1) per_sm = 1;
         cudaError_t e = cudaMemsetAsync(d_work_counter, 0, sizeof(int32_t), lc.stream);
         if (e != cudaSuccess) return e;
-        k_symbolic_bitmap<<<grid_for(h_counts[SYM_BITMAP], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
-            job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + SYM_BITMAP * stride, h_counts[SYM_BITMAP],
-            (int)window_bits, d_nnz, d_work_counter);
+        if (per_sm >= 2)
+            k_symbolic_bitmap<512><<<grid_for(h_counts[SYM_BITMAP], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
+                job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + SYM_BITMAP * stride, h_counts[SYM_BITMAP],
+                (int)window_bits, d_nnz, d_work_counter);
+        else                                           // one block per SM: make it a full 1024 threads
+            k_symbolic_bitmap<1024><<<grid_for(h_counts[SYM_BITMAP], 1, lc.sm_count), 1024, smem, lc.stream>>>(
+                job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + SYM_BITMAP * stride, h_counts[SYM_BITMAP],
+                (int)window_bits, d_nnz, d_work_counter);
         SB_LAUNCH_CHECK(lc);
     }
     return cudaSuccess;
@@ -432,34 +432,24 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
     if (h_counts[NUM_RANK]) {
         cudaError_t e = cudaMemsetAsync(d_work_counter, 0, sizeof(int32_t), lc.stream);
         if (e != cudaSuccess) return e;
-        // column window: all columns when the {bits, prefix} table (8 B per 32 columns) leaves room for a useful
-        // value array, else 2^19 columns (128 KB table)
-        const size_t max_dyn = g_smem_optin - 20480;                     // what sparse_kernels_configure allows
-        const size_t two_per_sm = g_smem_optin / 2 - 11264;              // dynamic bytes that still fit 2 blocks/SM
-        int64_t window = ((int64_t)job.B.cols + 31) & ~(int64_t)31;
-        if ((size_t)(window / 4) + 4096 * 8 > max_dyn) window = 1 << 19;
-        const size_t table_bytes = (size_t)(window / 4);
-        const size_t avail = (table_bytes + 4096 * 8 <= two_per_sm ? two_per_sm : max_dyn) - table_bytes;
-        int cap = (int)(avail / 8);
-        if (cap > 12288) cap = 12288;
-        const char* env_cap = getenv("SPGEMM_B200_RANK_CAP");
-        if (env_cap && atoi(env_cap) > 0 && atoi(env_cap) < cap) cap = atoi(env_cap);
-        cap &= ~31;
-        const char* env_mode = getenv("SPGEMM_B200_RANK_MODE");
-        const bool smem_acc = env_mode && atoi(env_mode) == 1;      // default: L2 reductions (faster as measured)
-        if (!smem_acc) cap = 0;
-        const size_t smem = (size_t)cap * 8 + table_bytes;
-        int per_sm = (int)((g_smem_optin + 1024) / (smem + 10240));
-        if (per_sm > 4) per_sm = 4;
-        if (per_sm < 1) per_sm = 1;
-        if (smem_acc)
-            k_numeric_rank<true><<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
+        // pair layout (8 B per 32 columns) while at least two blocks fit an SM; else the compact layout (5 B per
+        // 32 columns) with one 1024-thread block per SM and a window of up to 2^20 columns
+        const int64_t cols = ((int64_t)job.B.cols + 127) & ~(int64_t)127;
+        const size_t two_per_sm = g_smem_optin / 2 - 11264;
+        if ((size_t)(cols / 4) <= two_per_sm) {
+            const size_t smem = (size_t)(cols / 4);
+            int per_sm = (int)((g_smem_optin + 1024) / (smem + 10240));
+            if (per_sm > 4) per_sm = 4;
+            k_numeric_rank<false, 512><<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
                 job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_RANK * stride, h_counts[NUM_RANK],
-                (int)window, cap, c_ptr, c_idx, c_val, d_work_counter);
-        else
-            k_numeric_rank<false><<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
+                (int)cols, c_ptr, c_idx, c_val, d_work_counter);
+        } else {
+            const int64_t window = cols < (1 << 20) ? cols : (1 << 20);
+            const size_t smem = (size_t)(window / 8 + window / 32);
+            k_numeric_rank<true, 1024><<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count), 1024, smem, lc.stream>>>(
                 job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_RANK * stride, h_counts[NUM_RANK],
-                (int)window, cap, c_ptr, c_idx, c_val, d_work_counter);
+                (int)window, c_ptr, c_idx, c_val, d_work_counter);
+        }
         SB_LAUNCH_CHECK(lc);
     }
     return cudaSuccess;

@@ -105,6 +105,25 @@ def test_sparse_bins_mixed_rows():
     assert nnz_rows.max() > 16384 and nnz_rows.min() == 0        # dense-window and empty rows both present
 
 
+@pytest.mark.parametrize("n", [600_000, 1_800_000])
+def test_sparse_wide_matrices(n):
+    """Column counts beyond the pair-table layout: 600,000 columns take the compact rank table (one window),
+    1,800,000 take two column windows in both the symbolic bitmap and the numeric rank kernel."""
+    rng = np.random.default_rng(n)
+    b = sp.random(n, n, density=2.5 / n, format='csr', random_state=rng)
+    rows, cols = [], []
+    for i, c in enumerate([0, 3, 400, 1500, 5000, 900, 2500]):
+        rows += [i] * c
+        cols += list(rng.choice(n, size=c, replace=False))
+    a = sp.csr_matrix((rng.random(len(rows)), (rows, cols)), shape=(7, n))
+    got = sparse_matrix_multiply(a, b)
+    want = port.spgemm_csr(a, b)
+    assert_csr_equal(got, want, f"wide n={n}")
+    assert np.diff(got.indptr).max() > 768          # the block (rank) kernel was exercised
+    at = sp.csr_matrix((rng.random(len(rows)), (cols, rows)), shape=(n, 7))      # tall operand, narrow result
+    assert_csr_equal(sparse_matrix_multiply(a, at), port.spgemm_csr(a, at), "wide inner dimension")
+
+
 def test_unsorted_b_with_duplicates_large():
     """B with shuffled columns inside rows and repeated entries: the windowed kernels must fall back to filtering."""
     rng = np.random.default_rng(5)
