@@ -44,31 +44,25 @@ def triple_flops(h, q, upper=True, chunk=2000):
     """2 * (P1 + P2): P1 = products of H*Q, P2 = sum_i sum_{c in cols(T_i)} |{r >= i : H[r,c] != 0}| with
     T = H*Q merged (structure only), computed in row chunks."""
     p1 = count_products(h, q)
-    hp = sp.csr_matrix((np.ones(h.nnz, np.int8), h.indices, h.indptr), shape=h.shape)
-    qp = sp.csr_matrix((np.ones(q.nnz, np.int8), q.indices, q.indptr), shape=q.shape)
+    hp = sp.csr_matrix((np.ones(h.nnz, np.int32), h.indices, h.indptr), shape=h.shape)
+    qp = sp.csr_matrix((np.ones(q.nnz, np.int32), q.indices, q.indptr), shape=q.shape)
     ht = sp.csr_matrix(h.T)
     ht.sort_indices()
-    ht_len = np.diff(ht.indptr).astype(np.int64)
-    p2 = 0
     n = h.shape[0]
+    ht_ptr = ht.indptr.astype(np.int64)
+    ht_len = np.diff(ht_ptr)
+    # global sort key of every entry (c, r) of H^T: c * n + r  (rows of H^T are sorted, so keys are sorted)
+    keys = np.repeat(np.arange(ht.shape[0], dtype=np.int64), ht_len) * n + ht.indices
+    p2 = 0
     for r0 in range(0, n, chunk):
-        t = (hp[r0:r0 + chunk].astype(np.int32) @ qp.astype(np.int32)).tocsr()
+        t = (hp[r0:r0 + chunk] @ qp).tocsr()
+        cols = t.indices.astype(np.int64)
         if not upper:
-            p2 += int(ht_len[t.indices].sum())
+            p2 += int(ht_len[cols].sum())
             continue
-        rows = np.repeat(np.arange(r0, r0 + t.shape[0]), np.diff(t.indptr))
-        cols = t.indices
-        # entries of H^T row c with row index >= i: len - (number < i)
-        starts = ht.indptr[cols]
-        ends = ht.indptr[cols + 1]
-        # vectorised lower_bound inside each H^T row: rows of H^T are short, do it by cumulative compare
-        cnt = np.zeros(len(cols), dtype=np.int64)
-        maxlen = int((ends - starts).max()) if len(cols) else 0
-        for k in range(maxlen):
-            pos = starts + k
-            ok = pos < ends
-            cnt[ok] += ht.indices[pos[ok]] >= rows[ok]
-        p2 += int(cnt.sum())
+        rows = np.repeat(np.arange(r0, r0 + t.shape[0], dtype=np.int64), np.diff(t.indptr))
+        first_ge = np.searchsorted(keys, cols * n + rows, side="left")      # first entry of H^T[c,:] with r >= i
+        p2 += int((ht_ptr[cols + 1] - first_ge).sum())
     return 2 * (p1 + p2), p1, p2
 
 
@@ -259,6 +253,9 @@ def run_ours(args, w, name, info, flops, rank, world):
         torch.cuda.set_device(local)
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
+        box = [info, flops]
+        dist.broadcast_object_list(box, src=0)
+        info, flops = box
 
     a, b, kind, kw = w["a"], w["b"], w["kind"], w["kwargs"]
     sym = bool(kw.get("symmetric"))
@@ -434,7 +431,10 @@ def main():
 
     from sparse_matrix_mult_b200 import synthetic
     w = synthetic.workload(args.workload)
-    info, flops = describe(w, args.workload)
+    if rank == 0:
+        info, flops = describe(w, args.workload)       # counting products can take minutes for cfg5: once
+    else:
+        info, flops = None, None
     if args.impl == "reference":
         run_reference_arm(args, w, args.workload, info)
     else:
