@@ -637,8 +637,8 @@ int spgemm_b200_triple_dev(const spgemm_b200_mat* h, const spgemm_b200_mat* q, c
     }
     mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
     unsigned long long* d_cnt = nullptr;
-    if ((rc = dalloc(&d_cnt, 2))) { spgemm_b200_mat_free(own_ht); return rc; }
-    cudaError_t e = cudaMemsetAsync(d_cnt, 0, 16, g.stream);
+    if ((rc = dalloc(&d_cnt, 4))) { spgemm_b200_mat_free(own_ht); return rc; }
+    cudaError_t e = cudaMemsetAsync(d_cnt, 0, 32, g.stream);
     if (e == cudaSuccess)
         e = launch_triple(lctx(), view(h), view(q), view(ht), upper_only != 0, row_begin, row_end - row_begin, d_c, d_cnt,
                           env_mode("SPGEMM_B200_TRIPLE_MODE"));
@@ -680,9 +680,9 @@ int spgemm_b200_triple(int n, int k, const int32_t* h_indptr, const int32_t* h_i
     if ((rc = transpose_impl(h, &ht))) return done(rc);
     mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
     const size_t elems = (size_t)n * (size_t)n;
-    if ((rc = dalloc(&d_c, elems)) || (rc = dalloc(&d_cnt, 2))) return done(rc);
+    if ((rc = dalloc(&d_c, elems)) || (rc = dalloc(&d_cnt, 4))) return done(rc);
     const bool upper = mode != SPGEMM_B200_TRIPLE_REF_FULL;
-    cudaError_t e = cudaMemsetAsync(d_cnt, 0, 16, g.stream);
+    cudaError_t e = cudaMemsetAsync(d_cnt, 0, 32, g.stream);
     if (e == cudaSuccess) e = launch_triple(lctx(), view(h), view(q), view(ht), upper, 0, n, d_c, d_cnt, env_mode("SPGEMM_B200_TRIPLE_MODE"));
     if (e != cudaSuccess) return done(fail(SPGEMM_B200_ERR_CUDA, "triple kernel", e));
     mark(EV_NUMERIC);

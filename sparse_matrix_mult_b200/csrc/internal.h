@@ -80,7 +80,7 @@ cudaError_t dense_kernels_configure();
 // ---- triple.cu ----------------------------------------------------------------------------------
 cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht,
                           bool upper_only, int row_begin, int nrows, double* d_c,
-                          unsigned long long* d_counters /* [2]: P1, P2; may be null */, int mode);
+                          unsigned long long* d_counters /* [3], zeroed: P1, P2, row ticket */, int mode);
 cudaError_t triple_kernels_configure();
 
 }  // namespace sb

@@ -38,7 +38,7 @@ __device__ __forceinline__ void triple_stream_out(double* __restrict__ dst, cons
     if (tail < count && tid == nt - 1) st_stream_f64(dst + tail, src ? src[tail] : 0.0);
 }
 
-// counters[0] += expansion products (P1), counters[1] += scatter-adds performed (P2)
+// counters[0] += expansion products (P1), counters[1] += scatter-adds performed (P2); counters[2] = row ticket
 __device__ __forceinline__ void triple_flush_counters(unsigned long long p1, unsigned long long p2,
                                                       unsigned long long* s_cnt, unsigned long long* counters) {
     if (!counters) return;
@@ -98,19 +98,28 @@ k_triple_tiles(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, int tile_w, int n
 // Variant without a shared-memory tile: the block owns a whole row of C, streams zeros over it while the
 // gathers of H[i,:] are in flight, then adds every contribution with a float64 reduction that resolves in L2
 // (native RED.ADD.F64 -- the shared-memory path needs a compare-and-swap loop per add).
-constexpr int kTripleRedThreads = 256;
-
-template <bool UPPER>
-__global__ void __launch_bounds__(kTripleRedThreads)
+// The rows being accumulated must stay L2 resident (a reduction that misses L2 is a DRAM read-modify-write, ~8x
+// slower): the grid is persistent and sized so that rows-in-flight x 8n bytes fits a share of the 126 MB L2;
+// wide outputs therefore run one 1024-thread block per SM instead of eight 256-thread blocks.
+template <bool UPPER, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 k_triple_rows_red(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, double* __restrict__ C,
                   unsigned long long* __restrict__ counters) {
     __shared__ unsigned long long s_cnt[2];
-    __shared__ SegScratch<kTripleRedThreads> s_seg;
+    __shared__ SegScratch<THREADS> s_seg;
     const int n = H.rows;
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     unsigned long long p1 = 0, p2 = 0;
-    for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
+    __shared__ int s_row;
+    while (true) {
+        // rows are handed out in order through counters[2] (upper-triangle rows get cheaper towards the bottom,
+        // so in-order dynamic scheduling is longest-first)
+        if (threadIdx.x == 0) s_row = (int)atomicAdd(counters + 2, 1ULL);
+        __syncthreads();
+        const int r = s_row;
+        __syncthreads();
+        if (r >= nrows) break;
         const int i = row_begin + r;
         const int lo = UPPER ? i : 0;
         double* row = C + (size_t)r * n;
@@ -151,11 +160,25 @@ cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const
     if (nrows <= 0 || n <= 0) return cudaSuccess;
     if (mode == 0) mode = 2;
     if (mode == 2) {
-        const int grid = nrows;
-        if (upper_only)
-            k_triple_rows_red<true><<<grid, kTripleRedThreads, 0, lc.stream>>>(H, Q, Ht, row_begin, nrows, d_c, d_counters);
-        else
-            k_triple_rows_red<false><<<grid, kTripleRedThreads, 0, lc.stream>>>(H, Q, Ht, row_begin, nrows, d_c, d_counters);
+        const double l2_budget = 64.0e6;                                  // bytes of C rows in flight
+        const double row_bytes = 8.0 * n * (upper_only ? 0.6 : 1.0);      // upper rows touch [i, n) only
+        int rows_in_flight = (int)(l2_budget / row_bytes);
+        if (rows_in_flight < lc.sm_count) rows_in_flight = lc.sm_count;
+        const bool big = rows_in_flight < lc.sm_count * 4;                // few rows allowed: fat blocks
+        const int per_sm = big ? 1 : (rows_in_flight / lc.sm_count > 8 ? 8 : rows_in_flight / lc.sm_count);
+        int grid = lc.sm_count * per_sm;
+        if (grid > nrows) grid = nrows;
+        if (big) {
+            if (upper_only)
+                k_triple_rows_red<true, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, row_begin, nrows, d_c, d_counters);
+            else
+                k_triple_rows_red<false, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, row_begin, nrows, d_c, d_counters);
+        } else {
+            if (upper_only)
+                k_triple_rows_red<true, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, row_begin, nrows, d_c, d_counters);
+            else
+                k_triple_rows_red<false, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, row_begin, nrows, d_c, d_counters);
+        }
         SB_LAUNCH_CHECK(lc);
         return cudaSuccess;
     }
