@@ -255,6 +255,34 @@ cudaError_t launch_transpose_fill(const LaunchCtx& lc, const Csr& X, const int32
     return cudaSuccess;
 }
 
+// Sort the entries of every (short) row by DESCENDING column, in place: one thread per row, insertion sort.
+// Used on H^T: the triple product's upper-triangle contraction then reads a row of H^T from the front and stops
+// at the first entry below the diagonal.  Rows longer than 64 entries are left alone and clear *flag.
+__global__ void __launch_bounds__(256)
+k_sort_rows_desc(int rows, const int32_t* __restrict__ ptr, int32_t* __restrict__ idx, double* __restrict__ val,
+                 int32_t* __restrict__ flag) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int s = ptr[r], e = ptr[r + 1];
+    if (e - s <= 1) return;
+    if (e - s > 64) { *flag = 0; return; }
+    for (int a = s + 1; a < e; ++a) {
+        const int k = idx[a];
+        const double v = val[a];
+        int b = a - 1;
+        while (b >= s && idx[b] < k) { idx[b + 1] = idx[b]; val[b + 1] = val[b]; --b; }
+        idx[b + 1] = k;
+        val[b + 1] = v;
+    }
+}
+cudaError_t launch_sort_rows_desc(const LaunchCtx& lc, int rows, const int32_t* ptr, int32_t* idx, double* val,
+                                  int32_t* d_flag) {
+    if (rows <= 0) return cudaSuccess;
+    k_sort_rows_desc<<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, ptr, idx, val, d_flag);
+    SB_LAUNCH_CHECK(lc);
+    return cudaSuccess;
+}
+
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_narrow(const int64_t* __restrict__ in, int32_t* __restrict__ out, int n) {
@@ -272,7 +300,8 @@ cudaError_t launch_narrow_indptr(const LaunchCtx& lc, const int64_t* in, int32_t
 // Cost of row i of the triple product H Q H^T for the flop-balanced multi-GPU split:
 //   P1_i = sum over (i,j) in H of nnz(Q[j,:])                         (expansion of H[i,:] Q)
 //   P2_i = sum over those (j,c) of nnz(H^T[c,:])                      (contraction against H^T), scaled by the
-//          fraction (n - i) / n of columns kept when only the upper triangle is computed.
+//          fraction (n - i) / n of columns kept when only the upper triangle is computed; every product also
+//          pays one look at its row of H^T, hence 2 * P1.
 // One warp per row.
 __global__ void __launch_bounds__(256)
 k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, int64_t* __restrict__ costs) {
@@ -288,7 +317,7 @@ k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, int64_t* __restrict__ costs
     p2 = warp_sum(p2);
     if (lane_id() == 0) {
         if (upper_only) p2 = (long long)((double)p2 * (double)(H.rows - row) / (double)H.rows);
-        costs[row] = p1 + p2;
+        costs[row] = 2 * p1 + p2;
     }
 }
 cudaError_t launch_triple_costs(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool upper_only,

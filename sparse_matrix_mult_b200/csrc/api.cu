@@ -24,7 +24,8 @@ struct spgemm_b200_mat {
     int32_t* idx;
     double* val;
     bool owns;
-    int32_t* d_sorted;   // device flag, lazily computed (null = unknown)
+    int32_t* d_sorted;   // device flag, lazily computed (null = unknown): rows sorted by ascending column
+    int32_t* d_desc;     // device flag set by transpose: rows sorted by DESCENDING column (null = unknown)
 };
 struct spgemm_b200_result {
     int rows, cols;
@@ -160,7 +161,7 @@ int upload(int rows, int cols, const int32_t* ptr, const int32_t* idx, const dou
     if (nnz < 0) return fail(SPGEMM_B200_ERR_ARG, "indptr is not non-decreasing");
     if (nnz > 0 && (!idx || !val)) return fail(SPGEMM_B200_ERR_ARG, "null indices/values with nnz > 0");
     if (rows > 0 && ptr[0] != 0) return fail(SPGEMM_B200_ERR_ARG, "indptr[0] must be 0");
-    spgemm_b200_mat* m = new spgemm_b200_mat{rows, cols, nnz, nullptr, nullptr, nullptr, true, nullptr};
+    spgemm_b200_mat* m = new spgemm_b200_mat{rows, cols, nnz, nullptr, nullptr, nullptr, true, nullptr, nullptr};
     int rc;
     if ((rc = dalloc(&m->ptr, (size_t)rows + 1)) || (rc = dalloc(&m->idx, (size_t)nnz)) ||
         (rc = dalloc(&m->val, (size_t)nnz))) {
@@ -182,7 +183,7 @@ int upload(int rows, int cols, const int32_t* ptr, const int32_t* idx, const dou
 
 // Build X^T on the device (rows of the transpose are in arbitrary order).
 int transpose_impl(const spgemm_b200_mat* x, spgemm_b200_mat** out) {
-    spgemm_b200_mat* t = new spgemm_b200_mat{x->cols, x->rows, x->nnz, nullptr, nullptr, nullptr, true, nullptr};
+    spgemm_b200_mat* t = new spgemm_b200_mat{x->cols, x->rows, x->nnz, nullptr, nullptr, nullptr, true, nullptr, nullptr};
     int32_t *counts = nullptr, *cursor = nullptr;
     int64_t* tmp = nullptr;
     int rc;
@@ -198,6 +199,12 @@ int transpose_impl(const spgemm_b200_mat* x, spgemm_b200_mat** out) {
     if (e == cudaSuccess) e = launch_transpose_count(lc, view(x), x->nnz, counts);
     if (e == cudaSuccess) e = launch_scan_i32(lc, counts, t->ptr, t->rows, tmp);
     if (e == cudaSuccess) e = launch_transpose_fill(lc, view(x), t->ptr, cursor, t->idx, t->val);
+    // rows of the transpose come out in atomic order: sort them by descending column (see k_sort_rows_desc)
+    if (e == cudaSuccess && dalloc(&t->d_desc, 1) == SPGEMM_B200_OK) {
+        const int32_t one = 1;
+        e = cudaMemcpyAsync(t->d_desc, &one, 4, cudaMemcpyHostToDevice, g.stream);
+        if (e == cudaSuccess) e = launch_sort_rows_desc(lc, t->rows, t->ptr, t->idx, t->val, t->d_desc);
+    }
     dfree(counts); dfree(cursor); dfree(tmp);
     if (e != cudaSuccess) {
         spgemm_b200_mat_free(t);
@@ -446,7 +453,7 @@ int spgemm_b200_mat_wrap(int rows, int cols, int64_t nnz, const int32_t* d_indpt
     if (rc) return rc;
     if (!out || !d_indptr || rows < 0 || cols < 0 || nnz < 0) return fail(SPGEMM_B200_ERR_ARG, "mat_wrap: bad argument");
     *out = new spgemm_b200_mat{rows, cols, nnz, const_cast<int32_t*>(d_indptr), const_cast<int32_t*>(d_indices),
-                               const_cast<double*>(d_values), false, nullptr};
+                               const_cast<double*>(d_values), false, nullptr, nullptr};
     return SPGEMM_B200_OK;
 }
 
@@ -461,6 +468,7 @@ void spgemm_b200_mat_free(spgemm_b200_mat* m) {
     if (!m) return;
     if (m->owns) { dfree(m->ptr); dfree(m->idx); dfree(m->val); }
     dfree(m->d_sorted);
+    dfree(m->d_desc);
     delete m;
 }
 
@@ -640,7 +648,7 @@ int spgemm_b200_triple_dev(const spgemm_b200_mat* h, const spgemm_b200_mat* q, c
     if ((rc = dalloc(&d_cnt, 4))) { spgemm_b200_mat_free(own_ht); return rc; }
     cudaError_t e = cudaMemsetAsync(d_cnt, 0, 32, g.stream);
     if (e == cudaSuccess)
-        e = launch_triple(lctx(), view(h), view(q), view(ht), upper_only != 0, row_begin, row_end - row_begin, d_c, d_cnt,
+        e = launch_triple(lctx(), view(h), view(q), view(ht), ht->d_desc, upper_only != 0, row_begin, row_end - row_begin, d_c, d_cnt,
                           env_mode("SPGEMM_B200_TRIPLE_MODE"));
     mark(EV_NUMERIC); mark(EV_POST);
     unsigned long long* hc = reinterpret_cast<unsigned long long*>(static_cast<char*>(g.h_small) + 512);
@@ -683,7 +691,7 @@ int spgemm_b200_triple(int n, int k, const int32_t* h_indptr, const int32_t* h_i
     if ((rc = dalloc(&d_c, elems)) || (rc = dalloc(&d_cnt, 4))) return done(rc);
     const bool upper = mode != SPGEMM_B200_TRIPLE_REF_FULL;
     cudaError_t e = cudaMemsetAsync(d_cnt, 0, 32, g.stream);
-    if (e == cudaSuccess) e = launch_triple(lctx(), view(h), view(q), view(ht), upper, 0, n, d_c, d_cnt, env_mode("SPGEMM_B200_TRIPLE_MODE"));
+    if (e == cudaSuccess) e = launch_triple(lctx(), view(h), view(q), view(ht), ht->d_desc, upper, 0, n, d_c, d_cnt, env_mode("SPGEMM_B200_TRIPLE_MODE"));
     if (e != cudaSuccess) return done(fail(SPGEMM_B200_ERR_CUDA, "triple kernel", e));
     mark(EV_NUMERIC);
     if (mode == SPGEMM_B200_TRIPLE_REF_FULL) e = launch_symmetrize(lctx(), d_c, n);

@@ -49,6 +49,9 @@ cudaError_t launch_transpose_count(const LaunchCtx& lc, const Csr& X, int64_t nn
 cudaError_t launch_transpose_fill(const LaunchCtx& lc, const Csr& X, const int32_t* t_ptr, int32_t* d_cursor,
                                   int32_t* t_idx, double* t_val);
 
+// rows sorted by descending column, in place; *d_flag (preset to 1) is cleared when a row is too long to sort
+cudaError_t launch_sort_rows_desc(const LaunchCtx& lc, int rows, const int32_t* ptr, int32_t* idx, double* val,
+                                  int32_t* d_flag);
 cudaError_t launch_narrow_indptr(const LaunchCtx& lc, const int64_t* in, int32_t* out, int n);
 
 // cost model of the triple product rows (see spgemm_b200_row_costs)
@@ -78,7 +81,8 @@ cudaError_t launch_symmetrize(const LaunchCtx& lc, double* d_c, int n);
 cudaError_t dense_kernels_configure();
 
 // ---- triple.cu ----------------------------------------------------------------------------------
-cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht,
+// d_ht_desc: device flag, 1 when every row of Ht is sorted by descending column (null = unknown -> filter)
+cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, const int32_t* d_ht_desc,
                           bool upper_only, int row_begin, int nrows, double* d_c,
                           unsigned long long* d_counters /* [3], zeroed: P1, P2, row ticket */, int mode);
 cudaError_t triple_kernels_configure();

@@ -240,8 +240,9 @@ struct RankTable {
 template <bool COMPACT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_numeric_rank(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __restrict__ b_sorted_flag,
-               const int32_t* __restrict__ list, int count, int window, const int64_t* __restrict__ c_ptr,
-               int32_t* __restrict__ c_idx, double* __restrict__ c_val, int32_t* __restrict__ work_counter) {
+               const int32_t* __restrict__ list, int count, int stride, int window,
+               const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, double* __restrict__ c_val,
+               int32_t* __restrict__ work_counter) {
     extern __shared__ unsigned s_dynu[];
     RankTable<COMPACT> tab;
     tab.bits = s_dynu;
@@ -257,7 +258,10 @@ k_numeric_rank(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __res
         const int item = s_item;
         __syncthreads();
         if (item >= count) break;
-        const int r = __ldg(list + item), i = row_begin + r;
+        // Tickets are mapped to list positions by a stride coprime with `count`: the list is roughly in row order
+        // and on power-law inputs the heavy rows sit together; scattered, the rows in flight are a random sample
+        // and fewer multi-megabyte value slices compete for L2 at once (cfg 4: 257 -> 244 ms).
+        const int r = __ldg(list + (int)(((long long)item * stride) % count)), i = row_begin + r;
         const int a_begin = __ldg(A.ptr + i), a_end = __ldg(A.ptr + i + 1);
         const int lo = upper_only ? i : 0;
         int64_t out = __ldg(c_ptr + r);
@@ -432,6 +436,12 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
     if (h_counts[NUM_RANK]) {
         cudaError_t e = cudaMemsetAsync(d_work_counter, 0, sizeof(int32_t), lc.stream);
         if (e != cudaSuccess) return e;
+        // ticket -> list position stride: a prime that does not divide the count (so the map is a permutation)
+        int ticket_stride = 1;
+        for (int cand : {1000003, 999983, 999979, 7919, 104729}) {
+            if (h_counts[NUM_RANK] % cand != 0) { ticket_stride = cand % h_counts[NUM_RANK]; break; }
+        }
+        if (ticket_stride == 0) ticket_stride = 1;
         // pair layout (8 B per 32 columns) while at least two blocks fit an SM; else the compact layout (5 B per
         // 32 columns) with one 1024-thread block per SM and a window of up to 2^20 columns
         const int64_t cols = ((int64_t)job.B.cols + 127) & ~(int64_t)127;
@@ -442,13 +452,13 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
             if (per_sm > 4) per_sm = 4;
             k_numeric_rank<false, 512><<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
                 job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_RANK * stride, h_counts[NUM_RANK],
-                (int)cols, c_ptr, c_idx, c_val, d_work_counter);
+                ticket_stride, (int)cols, c_ptr, c_idx, c_val, d_work_counter);
         } else {
             const int64_t window = cols < (1 << 20) ? cols : (1 << 20);
             const size_t smem = (size_t)(window / 8 + window / 32);
             k_numeric_rank<true, 1024><<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count), 1024, smem, lc.stream>>>(
                 job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_RANK * stride, h_counts[NUM_RANK],
-                (int)window, c_ptr, c_idx, c_val, d_work_counter);
+                ticket_stride, (int)window, c_ptr, c_idx, c_val, d_work_counter);
         }
         SB_LAUNCH_CHECK(lc);
     }

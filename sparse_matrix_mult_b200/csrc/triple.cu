@@ -54,12 +54,13 @@ __device__ __forceinline__ void triple_flush_counters(unsigned long long p1, uns
 
 template <bool UPPER>
 __global__ void __launch_bounds__(kTripleThreads)
-k_triple_tiles(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, int tile_w, int ntiles, double* __restrict__ C,
-               unsigned long long* __restrict__ counters) {
+k_triple_tiles(Csr H, Csr Q, Csr Ht, const int32_t* __restrict__ ht_desc, int row_begin, int nrows, int tile_w,
+               int ntiles, double* __restrict__ C, unsigned long long* __restrict__ counters) {
     extern __shared__ double acc[];
     __shared__ unsigned long long s_cnt[2];
     __shared__ SegScratch<kTripleThreads> s_seg;
     const int n = H.rows;
+    const bool desc = ht_desc != nullptr && *ht_desc != 0;
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     unsigned long long p1 = 0, p2 = 0;
@@ -82,7 +83,8 @@ k_triple_tiles(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, int tile_w, int n
             const int s = __ldg(Ht.ptr + c), e = __ldg(Ht.ptr + c + 1);
             for (int q = s; q < e; ++q) {
                 const int k = __ldg(Ht.idx + q);
-                if (k >= lo && k < t1) {
+                if (k < lo) { if (desc) break; else continue; }     // descending rows: nothing useful follows
+                if (k < t1) {
                     atomicAdd(acc + (k - t0), w * __ldg(Ht.val + q));
                     ++p2;
                 }
@@ -103,11 +105,12 @@ k_triple_tiles(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, int tile_w, int n
 // wide outputs therefore run one 1024-thread block per SM instead of eight 256-thread blocks.
 template <bool UPPER, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_triple_rows_red(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, double* __restrict__ C,
-                  unsigned long long* __restrict__ counters) {
+k_triple_rows_red(Csr H, Csr Q, Csr Ht, const int32_t* __restrict__ ht_desc, int row_begin, int nrows,
+                  double* __restrict__ C, unsigned long long* __restrict__ counters) {
     __shared__ unsigned long long s_cnt[2];
     __shared__ SegScratch<THREADS> s_seg;
     const int n = H.rows;
+    const bool desc = ht_desc != nullptr && *ht_desc != 0;
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     unsigned long long p1 = 0, p2 = 0;
@@ -130,10 +133,9 @@ k_triple_rows_red(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, double* __rest
                                    const int s = __ldg(Ht.ptr + c), e = __ldg(Ht.ptr + c + 1);
                                    for (int q = s; q < e; ++q) {
                                        const int k = __ldg(Ht.idx + q);
-                                       if (k >= lo) {
-                                           atomicAdd(row + k, w * __ldg(Ht.val + q));
-                                           ++p2;
-                                       }
+                                       if (k < lo) { if (desc) break; else continue; }
+                                       atomicAdd(row + k, w * __ldg(Ht.val + q));
+                                       ++p2;
                                    }
                                });
     }
@@ -154,7 +156,8 @@ cudaError_t triple_kernels_configure() {
     return cudaFuncSetAttribute(k_triple_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
 }
 
-cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool upper_only,
+cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, const int32_t* d_ht_desc,
+                          bool upper_only,
                           int row_begin, int nrows, double* d_c, unsigned long long* d_counters, int mode) {
     const int n = H.rows;
     if (nrows <= 0 || n <= 0) return cudaSuccess;
@@ -170,14 +173,14 @@ cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const
         if (grid > nrows) grid = nrows;
         if (big) {
             if (upper_only)
-                k_triple_rows_red<true, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, row_begin, nrows, d_c, d_counters);
+                k_triple_rows_red<true, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, d_ht_desc, row_begin, nrows, d_c, d_counters);
             else
-                k_triple_rows_red<false, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, row_begin, nrows, d_c, d_counters);
+                k_triple_rows_red<false, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, d_ht_desc, row_begin, nrows, d_c, d_counters);
         } else {
             if (upper_only)
-                k_triple_rows_red<true, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, row_begin, nrows, d_c, d_counters);
+                k_triple_rows_red<true, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, d_ht_desc, row_begin, nrows, d_c, d_counters);
             else
-                k_triple_rows_red<false, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, row_begin, nrows, d_c, d_counters);
+                k_triple_rows_red<false, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, d_ht_desc, row_begin, nrows, d_c, d_counters);
         }
         SB_LAUNCH_CHECK(lc);
         return cudaSuccess;
@@ -194,10 +197,10 @@ cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const
     int64_t grid = (int64_t)lc.sm_count * per_sm * 8;
     if (grid > items) grid = items;
     if (upper_only)
-        k_triple_tiles<true><<<(unsigned)grid, kTripleThreads, smem, lc.stream>>>(H, Q, Ht, row_begin, nrows, tile_w,
+        k_triple_tiles<true><<<(unsigned)grid, kTripleThreads, smem, lc.stream>>>(H, Q, Ht, d_ht_desc, row_begin, nrows, tile_w,
                                                                                    ntiles, d_c, d_counters);
     else
-        k_triple_tiles<false><<<(unsigned)grid, kTripleThreads, smem, lc.stream>>>(H, Q, Ht, row_begin, nrows, tile_w,
+        k_triple_tiles<false><<<(unsigned)grid, kTripleThreads, smem, lc.stream>>>(H, Q, Ht, d_ht_desc, row_begin, nrows, tile_w,
                                                                                     ntiles, d_c, d_counters);
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
