@@ -368,9 +368,13 @@ def run_ours(args, w, name, info, flops, rank, world):
                 d2h_bytes = r.nbytes if isinstance(r, np.ndarray) else (r.data.nbytes + r.indices.nbytes + r.indptr.nbytes)
                 del r
             e2e_t = float(np.mean(e2e_ms))
+            st = dev.last_stats()           # of the last end-to-end call: bytes that actually crossed PCIe
             e2e = {"value": flops / (e2e_t * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_t,
-                   "h2d_bytes_per_step": int(csr_bytes(a) + (0 if (b is a and kind == "sparse") else csr_bytes(b))),
-                   "d2h_bytes_per_step": int(d2h_bytes), "timing": "host wall clock around sparse_matrix_multiply()"}
+                   "h2d_bytes_per_step": int(st["bytes_h2d"]), "d2h_bytes_per_step": int(st["bytes_d2h"]),
+                   "result_bytes": int(d2h_bytes),
+                   "device_ms": {k: round(st[k], 3) for k in ("ms_h2d", "ms_analysis", "ms_symbolic", "ms_numeric",
+                                                               "ms_post", "ms_d2h", "ms_total")},
+                   "timing": "host wall clock around sparse_matrix_multiply()"}
         except OverflowError as ex:       # nnz(C) >= 2^31 cannot be returned as a SciPy int32 CSR (BASELINE cfg4)
             e2e = {"value": None, "unit": UNIT, "unavailable": str(ex)}
     else:

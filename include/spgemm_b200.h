@@ -61,6 +61,9 @@ typedef struct {
     int64_t bytes_min;     /* algorithmic (compulsory) bytes of the compute phase, SURVEY.md 8(d)      */
     int32_t launches;      /* kernels launched by this library during the call                         */
     int32_t device;        /* CUDA device ordinal used                                                 */
+    int64_t bytes_h2d;     /* bytes copied host -> device by the call                                  */
+    int64_t bytes_d2h;     /* bytes copied device -> host by the call (upper trapezoids only for the
+                              symmetric dense modes: the zeros below the diagonal are written by the host) */
 } spgemm_b200_stats;
 
 /* ---- library / device ------------------------------------------------------------------------- */

@@ -7,6 +7,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -177,6 +178,7 @@ int upload(int rows, int cols, const int32_t* ptr, const int32_t* idx, const dou
         spgemm_b200_mat_free(m);
         return fail(SPGEMM_B200_ERR_CUDA, "operand upload", e);
     }
+    g.stats.bytes_h2d += csr_bytes(rows, nnz);
     *out = m;
     return SPGEMM_B200_OK;
 }
@@ -212,6 +214,46 @@ int transpose_impl(const spgemm_b200_mat* x, spgemm_b200_mat** out) {
     }
     *out = t;
     return SPGEMM_B200_OK;
+}
+
+// Device -> host copy of an n x n result whose strictly lower triangle is known to be zero (symmetric dense mode,
+// triple product): only the upper trapezoids cross PCIe -- row block [r0, r1) sends columns [r0, n) as one 2-D
+// copy -- while host threads zero the rectangles to their left.  Halves the bytes on the link, which is what
+// bounds these modes end to end (3.2 GB at ~55 GB/s for BASELINE config 2).
+cudaError_t d2h_upper(const double* d_c, int n, double* c_host) {
+    if (n <= 0) return cudaSuccess;
+    {
+        const int nb = n < 64 ? 1 : 64, st = (n + nb - 1) / nb;
+        for (int r0 = 0; r0 < n; r0 += st) g.stats.bytes_d2h += (int64_t)(n - r0) * ((r0 + st < n ? r0 + st : n) - r0) * 8;
+    }
+    const int blocks = n < 64 ? 1 : 64;
+    const int step = (n + blocks - 1) / blocks;
+    cudaError_t err = cudaSuccess;
+    for (int r0 = 0; r0 < n && err == cudaSuccess; r0 += step) {
+        const int r1 = r0 + step < n ? r0 + step : n;
+        err = cudaMemcpy2DAsync(c_host + (size_t)r0 * n + r0, (size_t)n * 8, d_c + (size_t)r0 * n + r0, (size_t)n * 8,
+                                (size_t)(n - r0) * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, g.stream);
+    }
+    // zero the lower-left rectangles on the host meanwhile (rows are split evenly by AREA over the threads)
+    unsigned hw = std::thread::hardware_concurrency();
+    int nthreads = hw == 0 ? 4 : (hw > 8 ? 8 : (int)hw);     // measured: flat beyond 4-8 threads (~40 GB/s)
+    if (const char* ev = getenv("SPGEMM_B200_ZERO_THREADS")) nthreads = atoi(ev);      // 0 = skip (experiments only)
+    if ((size_t)n * n < ((size_t)1 << 22) && nthreads > 1) nthreads = 1;
+    auto zero_rows = [=](int t) {
+        // thread t takes row blocks t, t + nthreads, ... (interleaved: equal area per thread)
+        int b = 0;
+        for (int r0 = 0; r0 < n; r0 += step, ++b) {
+            if (b % nthreads != t || r0 == 0) continue;
+            const int r1 = r0 + step < n ? r0 + step : n;
+            for (int r = r0; r < r1; ++r) memset(c_host + (size_t)r * n, 0, (size_t)r0 * 8);
+        }
+    };
+    if (nthreads <= 0) return err;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(zero_rows, t);
+    zero_rows(0);
+    for (auto& th : pool) th.join();
+    return err;
 }
 
 // Sparse product of rows [r0, r1).  Records EV_ANALYSIS / EV_SYMBOLIC / EV_NUMERIC.
@@ -549,6 +591,7 @@ int spgemm_b200_result_copy(const spgemm_b200_result* r, void* indptr, int index
     dfree(narrow);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
+    g.stats.bytes_d2h += (int64_t)(r->rows + 1) * (index64 ? 8 : 4) + r->nnz * 12;
     g.stats.ms_d2h += ms;
     g.stats.ms_total += ms;
     g.stats.launches = g.launches;
@@ -616,7 +659,8 @@ int spgemm_b200_dense(int m, int k, int n, const int32_t* a_indptr, const int32_
     }
     mark(EV_POST);
     if (elems) {
-        e = cudaMemcpyAsync(c_host, d_c, elems * 8, cudaMemcpyDeviceToHost, g.stream);
+        if (upper_only && !mirror && m == n) e = d2h_upper(d_c, n, c_host);
+        else { e = cudaMemcpyAsync(c_host, d_c, elems * 8, cudaMemcpyDeviceToHost, g.stream); g.stats.bytes_d2h += (int64_t)elems * 8; }
         if (e != cudaSuccess) return done(fail(SPGEMM_B200_ERR_CUDA, "dense result copy", e));
     }
     mark(EV_D2H);
@@ -700,7 +744,10 @@ int spgemm_b200_triple(int n, int k, const int32_t* h_indptr, const int32_t* h_i
     mark(EV_POST);
     unsigned long long* hc = reinterpret_cast<unsigned long long*>(static_cast<char*>(g.h_small) + 512);
     e = cudaMemcpyAsync(hc, d_cnt, 16, cudaMemcpyDeviceToHost, g.stream);
-    if (e == cudaSuccess && elems) e = cudaMemcpyAsync(c_host, d_c, elems * 8, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess && elems) {
+        if (mode == SPGEMM_B200_TRIPLE_UPPER) e = d2h_upper(d_c, n, c_host);
+        else { e = cudaMemcpyAsync(c_host, d_c, elems * 8, cudaMemcpyDeviceToHost, g.stream); g.stats.bytes_d2h += (int64_t)elems * 8; }
+    }
     mark(EV_D2H);
     if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
     if (e != cudaSuccess) return done(fail(SPGEMM_B200_ERR_CUDA, "triple result copy", e));

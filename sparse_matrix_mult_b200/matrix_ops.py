@@ -33,7 +33,8 @@ class Stats(ctypes.Structure):
     _fields_ = [("ms_h2d", ctypes.c_double), ("ms_analysis", ctypes.c_double), ("ms_symbolic", ctypes.c_double),
                 ("ms_numeric", ctypes.c_double), ("ms_post", ctypes.c_double), ("ms_d2h", ctypes.c_double),
                 ("ms_total", ctypes.c_double), ("products", ctypes.c_int64), ("nnz_c", ctypes.c_int64),
-                ("bytes_min", ctypes.c_int64), ("launches", ctypes.c_int32), ("device", ctypes.c_int32)]
+                ("bytes_min", ctypes.c_int64), ("launches", ctypes.c_int32), ("device", ctypes.c_int32),
+                ("bytes_h2d", ctypes.c_int64), ("bytes_d2h", ctypes.c_int64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
