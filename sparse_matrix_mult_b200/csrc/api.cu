@@ -1,6 +1,8 @@
 // api.cu -- the C ABI of libspgemm_b200.so (include/spgemm_b200.h): context, memory, orchestration.
 #include <cuda_runtime.h>
 
+#include <emmintrin.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -216,6 +218,24 @@ int transpose_impl(const spgemm_b200_mat* x, spgemm_b200_mat** out) {
     return SPGEMM_B200_OK;
 }
 
+// Zero `count` doubles with non-temporal stores: the destination is not read first (memset below its internal
+// threshold write-allocates, doubling the memory traffic) and the zeros do not displace the cache.
+static void zero_nt(double* p, size_t count) {
+    while (count && (reinterpret_cast<uintptr_t>(p) & 15)) { *p++ = 0.0; --count; }
+    __m128i z = _mm_setzero_si128();
+    __m128i* v = reinterpret_cast<__m128i*>(p);
+    size_t nv = count / 2;
+    size_t i = 0;
+    for (; i + 4 <= nv; i += 4) {
+        _mm_stream_si128(v + i, z);
+        _mm_stream_si128(v + i + 1, z);
+        _mm_stream_si128(v + i + 2, z);
+        _mm_stream_si128(v + i + 3, z);
+    }
+    for (; i < nv; ++i) _mm_stream_si128(v + i, z);
+    if (count & 1) p[count - 1] = 0.0;
+}
+
 // Device -> host copy of an n x n result whose strictly lower triangle is known to be zero (symmetric dense mode,
 // triple product): only the upper trapezoids cross PCIe -- row block [r0, r1) sends columns [r0, n) as one 2-D
 // copy -- while host threads zero the rectangles to their left.  Halves the bytes on the link, which is what
@@ -245,8 +265,9 @@ cudaError_t d2h_upper(const double* d_c, int n, double* c_host) {
         for (int r0 = 0; r0 < n; r0 += step, ++b) {
             if (b % nthreads != t || r0 == 0) continue;
             const int r1 = r0 + step < n ? r0 + step : n;
-            for (int r = r0; r < r1; ++r) memset(c_host + (size_t)r * n, 0, (size_t)r0 * 8);
+            for (int r = r0; r < r1; ++r) zero_nt(c_host + (size_t)r * n, (size_t)r0);
         }
+        _mm_sfence();
     };
     if (nthreads <= 0) return err;
     std::vector<std::thread> pool;
