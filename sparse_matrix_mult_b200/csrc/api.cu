@@ -49,6 +49,7 @@ struct Ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev[EV_COUNT] = {};
     bool ev_pending = false;
+    unsigned ev_mask = 0;            // which events were recorded by the current call
     spgemm_b200_stats stats = {};
     int launches = 0;
     void* h_small = nullptr;     // 4 KB pinned staging for counters
@@ -116,30 +117,49 @@ double products_per_out(const spgemm_b200_mat* a, const spgemm_b200_mat* b) {
     return (double)a->nnz * ((double)b->nnz / (double)b->rows) / out;
 }
 
-void begin_call() {
+void mark(int ev) {
+    cudaEventRecord(g.ev[ev], g.stream);
+    g.ev_mask |= 1u << ev;
+}
+// `lean` calls (device-resident entry points, which may sit inside a tight timed loop) record only the events
+// around their kernels; an unrecorded phase boundary coincides with the previous recorded one.
+void begin_call(bool lean = false) {
     g.launches = 0;
     memset(&g.stats, 0, sizeof g.stats);
     g.stats.device = g.device;
-    cudaEventRecord(g.ev[EV_START], g.stream);
+    g.ev_mask = 0;
+    if (!lean) mark(EV_START);
     g.ev_pending = true;
 }
-void mark(int ev) { cudaEventRecord(g.ev[ev], g.stream); }
 
-// fold event times into g.stats (blocks until the last event)
+// fold event times into g.stats (blocks until the last recorded event)
 void finish_stats() {
     if (!g.ev_pending) return;
-    cudaEventSynchronize(g.ev[EV_D2H]);
-    float ms = 0.f;
-    auto el = [&](int a, int b) { ms = 0.f; cudaEventElapsedTime(&ms, g.ev[a], g.ev[b]); return (double)ms; };
-    g.stats.ms_h2d = el(EV_START, EV_H2D);
-    g.stats.ms_analysis = el(EV_H2D, EV_ANALYSIS);
-    g.stats.ms_symbolic = el(EV_ANALYSIS, EV_SYMBOLIC);
-    g.stats.ms_numeric = el(EV_SYMBOLIC, EV_NUMERIC);
-    g.stats.ms_post = el(EV_NUMERIC, EV_POST);
-    g.stats.ms_d2h += el(EV_POST, EV_D2H);
-    g.stats.ms_total += el(EV_START, EV_D2H);
-    g.stats.launches = g.launches;
     g.ev_pending = false;
+    g.stats.launches = g.launches;
+    if (!g.ev_mask) return;
+    int last = 0, first = EV_COUNT;
+    for (int i = 0; i < EV_COUNT; ++i) if (g.ev_mask & (1u << i)) { last = i; if (first == EV_COUNT) first = i; }
+    cudaEventSynchronize(g.ev[last]);
+    // time of phase ending at event b = elapsed since the closest recorded event before it
+    auto phase = [&](int b) {
+        if (!(g.ev_mask & (1u << b))) return 0.0;
+        int a = b - 1;
+        while (a >= 0 && !(g.ev_mask & (1u << a))) --a;
+        if (a < 0) return 0.0;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g.ev[a], g.ev[b]);
+        return (double)ms;
+    };
+    g.stats.ms_h2d = phase(EV_H2D);
+    g.stats.ms_analysis = phase(EV_ANALYSIS);
+    g.stats.ms_symbolic = phase(EV_SYMBOLIC);
+    g.stats.ms_numeric = phase(EV_NUMERIC);
+    g.stats.ms_post = phase(EV_POST);
+    g.stats.ms_d2h += phase(EV_D2H);
+    float tot = 0.f;
+    if (first != last) cudaEventElapsedTime(&tot, g.ev[first], g.ev[last]);
+    g.stats.ms_total += tot;
 }
 
 int ensure_sorted_flag(spgemm_b200_mat* m) {
@@ -634,14 +654,16 @@ int spgemm_b200_dense_dev(const spgemm_b200_mat* a, const spgemm_b200_mat* b, in
     if (a->cols != b->rows) return fail(SPGEMM_B200_ERR_ARG, "dense_dev: inner dimensions differ");
     if (row_end < 0) { row_begin = 0; row_end = a->rows; }
     if (row_begin < 0 || row_end > a->rows || row_begin > row_end) return fail(SPGEMM_B200_ERR_ARG, "dense_dev: bad row range");
-    begin_call();
-    mark(EV_H2D);
-    if ((rc = ensure_sorted_flag(const_cast<spgemm_b200_mat*>(b)))) return rc;
-    mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
+    begin_call(true);
+    if (!b->d_sorted) {
+        mark(EV_H2D);
+        if ((rc = ensure_sorted_flag(const_cast<spgemm_b200_mat*>(b)))) return rc;
+    }
+    mark(EV_SYMBOLIC);
     cudaError_t de = launch_dense(lctx(), view(a), view(b), b->d_sorted, upper_only != 0, row_begin, row_end - row_begin,
                                   d_c, env_mode("SPGEMM_B200_DENSE_MODE"), products_per_out(a, b));
     if (de != cudaSuccess) return fail(SPGEMM_B200_ERR_CUDA, "dense kernel", de);
-    mark(EV_NUMERIC); mark(EV_POST); mark(EV_D2H);
+    mark(EV_NUMERIC);
     g.stats.nnz_c = (int64_t)(row_end - row_begin) * b->cols;
     g.stats.bytes_min = csr_bytes(a->rows, a->nnz) + csr_bytes(b->rows, b->nnz) + 8 * g.stats.nnz_c;
     return SPGEMM_B200_OK;
