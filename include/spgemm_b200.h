@@ -199,6 +199,17 @@ SPGEMM_B200_API int   spgemm_b200_copy_to_device(void *d_dst, const void *host_s
 /* device -> device on the library stream, asynchronous */
 SPGEMM_B200_API int   spgemm_b200_copy_on_device(void *d_dst, const void *d_src, size_t bytes);
 
+/* ---- peer memory (one process per GPU on one NVLink/NVSwitch box) -------------------------------------
+   A rank allocates its result buffer with spgemm_b200_shared_alloc, exports it, and the other ranks map it
+   with spgemm_b200_ipc_open: the row-range entry points above then WRITE THEIR ROWS STRAIGHT INTO THAT BUFFER
+   over NVLink (the kernels only see a pointer), which fuses the gather-to-rank-0 into the compute kernel. */
+#define SPGEMM_B200_IPC_HANDLE_BYTES 64
+SPGEMM_B200_API void *spgemm_b200_shared_alloc(size_t bytes);                 /* cudaMalloc: exportable   */
+SPGEMM_B200_API void  spgemm_b200_shared_free(void *d_ptr);
+SPGEMM_B200_API int   spgemm_b200_ipc_export(const void *d_ptr, unsigned char *handle /* 64 bytes */);
+SPGEMM_B200_API int   spgemm_b200_ipc_open(const unsigned char *handle /* 64 bytes */, void **d_ptr);
+SPGEMM_B200_API int   spgemm_b200_ipc_close(void *d_ptr);
+
 /* Make the library launch on `stream` (a cudaStream_t; NULL restores the library's own stream). */
 SPGEMM_B200_API int spgemm_b200_set_stream(void *stream);
 

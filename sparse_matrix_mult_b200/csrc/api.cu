@@ -852,6 +852,42 @@ int spgemm_b200_copy_on_device(void* d_dst, const void* d_src, size_t bytes) {
     return SPGEMM_B200_OK;
 }
 
+// ---- peer memory ---------------------------------------------------------------------------------------------
+void* spgemm_b200_shared_alloc(size_t bytes) {
+    if (ensure_init()) return nullptr;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { fail(SPGEMM_B200_ERR_CUDA, "shared_alloc", e); return nullptr; }
+    return p;
+}
+void spgemm_b200_shared_free(void* d_ptr) {
+    if (g.ready && d_ptr) cudaFree(d_ptr);
+}
+int spgemm_b200_ipc_export(const void* d_ptr, unsigned char* handle) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!d_ptr || !handle) return fail(SPGEMM_B200_ERR_ARG, "ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SPGEMM_B200_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+    memcpy(handle, &h, sizeof h);
+    return SPGEMM_B200_OK;
+}
+int spgemm_b200_ipc_open(const unsigned char* handle, void** d_ptr) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!handle || !d_ptr) return fail(SPGEMM_B200_ERR_ARG, "ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SPGEMM_B200_OK;
+}
+int spgemm_b200_ipc_close(void* d_ptr) {
+    if (!g.ready || !d_ptr) return SPGEMM_B200_OK;
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return SPGEMM_B200_OK;
+}
+
 // ---- stopwatch / L2 flush ------------------------------------------------------------------------------------
 static cudaEvent_t t_ev0 = nullptr, t_ev1 = nullptr;
 static void* g_flush_buf = nullptr;

@@ -146,6 +146,40 @@ class DeviceDense:
             pass
 
 
+class SharedDense:
+    """rows x cols float64 buffer that other ranks on the box can map (CUDA IPC) and write into over NVLink."""
+
+    def __init__(self, rows, cols, ptr=None, owner=True):
+        lib = matrix_ops.get_lib()
+        self.shape, self.nbytes, self.owner = (int(rows), int(cols)), int(rows) * int(cols) * 8, owner
+        self.ptr = ptr if ptr is not None else lib.spgemm_b200_shared_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError(lib.spgemm_b200_last_error().decode(errors="replace"))
+
+    def export(self):
+        buf = ctypes.create_string_buffer(64)
+        _check(matrix_ops.get_lib().spgemm_b200_ipc_export(_vp(self.ptr), buf), "spgemm_b200_ipc_export")
+        return buf.raw
+
+    @classmethod
+    def open(cls, handle, rows, cols):
+        p = _vp()
+        _check(matrix_ops.get_lib().spgemm_b200_ipc_open(handle, ctypes.byref(p)), "spgemm_b200_ipc_open")
+        return cls(rows, cols, ptr=p.value, owner=False)
+
+    def row_ptr(self, r):
+        return self.ptr + int(r) * self.shape[1] * 8
+
+    def close(self):
+        lib = matrix_ops.get_lib()
+        if self.ptr:
+            if self.owner:
+                lib.spgemm_b200_shared_free(_vp(self.ptr))
+            else:
+                lib.spgemm_b200_ipc_close(_vp(self.ptr))
+            self.ptr = None
+
+
 def _rows(a, row_begin, row_end):
     if row_end is None:
         return 0, a.shape[0]

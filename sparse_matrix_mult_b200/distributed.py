@@ -14,6 +14,8 @@ triple product whose rows get cheaper towards the bottom.
 The compute callback is injected so that the host-side logic (partition, broadcast packing, gather offsets) is
 testable on CPU with the gloo backend and the oracle as the per-rank compute (tests/test_distributed_cpu.py).
 """
+import os
+
 import numpy as np
 import scipy.sparse as sp
 import torch
@@ -235,6 +237,51 @@ def cuda_partition(a_t, b_t, kind, upper_only, world):
     return bounds.astype(np.int64)
 
 
+# ------------------------------------------------------------------------------------------------------
+# fused compute + gather: every rank's kernel writes its rows straight into rank 0's buffer over NVLink
+_peer_cache = {}
+
+
+def multiply_sharded_peer(matrix_a, matrix_b, kind, upper_only, device):
+    """Dense / triple product with the gather fused into the compute kernels: rank 0 owns an IPC-exported result
+    buffer, the other ranks map it, and the row-range kernels of every rank store (and reduce) directly into
+    their row slab of it -- peer stores over NVLink, no staging buffer and no separate gather collective.
+    Returns a device.SharedDense on rank 0 (valid until the next call with another shape), None elsewhere."""
+    from . import device as dev
+    assert kind in ("dense", "triple")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    a_t = broadcast_csr(matrix_a, device)
+    b_t = broadcast_csr(matrix_b, device)
+    rows = a_t[0][0]
+    ncols = rows if kind == "triple" else b_t[0][1]
+    key = (rows, ncols)
+    if key not in _peer_cache:                       # IPC mapping is expensive: once per result shape
+        for old in _peer_cache.values():
+            old.close()
+        _peer_cache.clear()
+        handle = torch.zeros(64, dtype=torch.uint8, device=device)
+        if rank == 0:
+            buf = dev.SharedDense(rows, ncols)
+            handle.copy_(torch.frombuffer(bytearray(buf.export()), dtype=torch.uint8))
+        dist.broadcast(handle, src=0)
+        if rank != 0:
+            buf = dev.SharedDense.open(bytes(handle.cpu().numpy().tobytes()), rows, ncols)
+        _peer_cache[key] = buf
+    buf = _peer_cache[key]
+    bounds = cuda_partition(a_t, b_t, kind, upper_only, world)
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    dev.set_stream(torch.cuda.current_stream().cuda_stream)
+    A, B = _wrap(dev, a_t), _wrap(dev, b_t)
+    if r1 > r0:
+        if kind == "dense":
+            dev.spgemm_dense(A, B, upper_only, r0, r1, out=buf.row_ptr(r0))
+        else:
+            dev.triple_product(A, B, None, upper_only, r0, r1, out=buf.row_ptr(r0))
+    dev.synchronize()                                # this rank's peer stores are complete
+    dist.barrier()                                   # ... and so are everybody else's
+    return buf if rank == 0 else None
+
+
 def bench_e2e(args, w, flops, rank, world, csr_bytes):
     """e2e at N GPUs: rank 0 starts from HOST operands and ends with a HOST result; every step does
     H2D on rank 0 (inside broadcast_csr) -> NCCL broadcast -> sharded compute -> gather to rank 0 -> D2H."""
@@ -252,18 +299,28 @@ def bench_e2e(args, w, flops, rank, world, csr_bytes):
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        out = multiply_sharded(a, b, kind, upper, device, fn, partition=cuda_partition)
-        if rank == 0:
-            # device -> pinned host arrays from the library's cache (what the single-GPU API returns too)
-            outs = out if kind == "sparse" else (out,)
-            d2h, host = 0, []
-            for t in outs:
-                h = _result_array(tuple(t.shape), {torch.int64: np.int64, torch.int32: np.int32,
-                                                   torch.float64: np.float64}[t.dtype])
-                dev.copy_to_host(h, t.data_ptr())
-                host.append(h)
-                d2h += h.nbytes
-            del host
+        if kind == "dense" and os.environ.get("SPGEMM_B200_GATHER", "peer") == "peer":
+            out = multiply_sharded_peer(a, b, kind, upper, device)          # gather fused into the kernels
+            gather = "peer stores over NVLink from inside the compute kernels (CUDA IPC)"
+            if rank == 0:
+                h = _result_array(out.shape, np.float64)
+                dev.copy_to_host(h, out.ptr)
+                d2h = h.nbytes
+                del h
+        else:
+            out = multiply_sharded(a, b, kind, upper, device, fn, partition=cuda_partition)
+            gather = "grouped NCCL isend/irecv of row blocks to rank 0"
+            if rank == 0:
+                # device -> pinned host arrays from the library's cache (what the single-GPU API returns too)
+                outs = out if kind == "sparse" else (out,)
+                d2h, host = 0, []
+                for t in outs:
+                    h = _result_array(tuple(t.shape), {torch.int64: np.int64, torch.int32: np.int32,
+                                                       torch.float64: np.float64}[t.dtype])
+                    dev.copy_to_host(h, t.data_ptr())
+                    host.append(h)
+                    d2h += h.nbytes
+                del host
         torch.cuda.synchronize()
         dist.barrier()
         if it >= 2:
@@ -276,4 +333,5 @@ def bench_e2e(args, w, flops, rank, world, csr_bytes):
         return None
     return {"value": flops / sec / 1e9, "unit": "GFLOP/s", "ms_per_step": sec * 1e3,
             "h2d_bytes_per_step": int(csr_bytes(w["a"]) + csr_bytes(w["b"])), "d2h_bytes_per_step": int(d2h),
+            "gather": gather,
             "timing": "host wall clock on rank 0 incl. H2D, NCCL broadcast, sharded kernels, gather to rank 0, D2H"}

@@ -112,6 +112,13 @@ class MatrixOpsLibrary:
         L.spgemm_b200_copy_to_host.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.spgemm_b200_copy_to_device.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.spgemm_b200_copy_on_device.argtypes = [_vp, _vp, ctypes.c_size_t]
+        L.spgemm_b200_shared_alloc.argtypes = [ctypes.c_size_t]
+        L.spgemm_b200_shared_alloc.restype = _vp
+        L.spgemm_b200_shared_free.argtypes = [_vp]
+        L.spgemm_b200_shared_free.restype = None
+        L.spgemm_b200_ipc_export.argtypes = [_vp, ctypes.c_char_p]
+        L.spgemm_b200_ipc_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(_vp)]
+        L.spgemm_b200_ipc_close.argtypes = [_vp]
         L.spgemm_b200_set_stream.argtypes = [_vp]
         L.spgemm_b200_timer_stop.argtypes = [ctypes.POINTER(ctypes.c_double)]
 
