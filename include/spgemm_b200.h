@@ -196,6 +196,9 @@ SPGEMM_B200_API void *spgemm_b200_device_alloc(size_t bytes);
 SPGEMM_B200_API void  spgemm_b200_device_free(void *d_ptr);
 SPGEMM_B200_API int   spgemm_b200_copy_to_host(void *host_dst, const void *d_src, size_t bytes);
 SPGEMM_B200_API int   spgemm_b200_copy_to_device(void *d_dst, const void *host_src, size_t bytes);
+/* n x n device matrix whose strictly lower triangle is zero -> host: only the upper trapezoids cross PCIe, the
+   rest is zeroed by host threads (what spgemm_b200_dense / _triple do for their symmetric modes); synchronous */
+SPGEMM_B200_API int   spgemm_b200_copy_upper_to_host(double *host_dst, const double *d_src, int n);
 /* device -> device on the library stream, asynchronous */
 SPGEMM_B200_API int   spgemm_b200_copy_on_device(void *d_dst, const void *d_src, size_t bytes);
 

@@ -844,6 +844,15 @@ int spgemm_b200_copy_to_device(void* d_dst, const void* host_src, size_t bytes) 
     return SPGEMM_B200_OK;
 }
 
+int spgemm_b200_copy_upper_to_host(double* host_dst, const double* d_src, int n) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (n > 0 && (!host_dst || !d_src)) return fail(SPGEMM_B200_ERR_ARG, "copy_upper_to_host: null pointer");
+    CU(d2h_upper(d_src, n, host_dst));
+    CU(cudaStreamSynchronize(g.stream));
+    return SPGEMM_B200_OK;
+}
+
 int spgemm_b200_copy_on_device(void* d_dst, const void* d_src, size_t bytes) {
     int rc = ensure_init();
     if (rc) return rc;

@@ -36,6 +36,13 @@ def copy_to_host(host_array, src_ptr):
                                                          host_array.nbytes), "spgemm_b200_copy_to_host")
 
 
+def copy_upper_to_host(host_array, src_ptr):
+    """n x n device matrix with a zero strictly-lower triangle -> host ndarray, sending only the upper trapezoids."""
+    n = host_array.shape[0]
+    _check(matrix_ops.get_lib().spgemm_b200_copy_upper_to_host(host_array.ctypes.data_as(_vp), _vp(src_ptr), n),
+           "spgemm_b200_copy_upper_to_host")
+
+
 def synchronize():
     _check(matrix_ops.get_lib().spgemm_b200_synchronize(), "spgemm_b200_synchronize")
 

@@ -304,8 +304,11 @@ def bench_e2e(args, w, flops, rank, world, csr_bytes):
             gather = "peer stores over NVLink from inside the compute kernels (CUDA IPC)"
             if rank == 0:
                 h = _result_array(out.shape, np.float64)
-                dev.copy_to_host(h, out.ptr)
-                d2h = h.nbytes
+                if upper and out.shape[0] == out.shape[1]:
+                    dev.copy_upper_to_host(h, out.ptr)
+                else:
+                    dev.copy_to_host(h, out.ptr)
+                d2h = int(dev.last_stats()["bytes_d2h"]) or h.nbytes
                 del h
         else:
             out = multiply_sharded(a, b, kind, upper, device, fn, partition=cuda_partition)
@@ -317,7 +320,10 @@ def bench_e2e(args, w, flops, rank, world, csr_bytes):
                 for t in outs:
                     h = _result_array(tuple(t.shape), {torch.int64: np.int64, torch.int32: np.int32,
                                                        torch.float64: np.float64}[t.dtype])
-                    dev.copy_to_host(h, t.data_ptr())
+                    if kind != "sparse" and upper and t.shape[0] == t.shape[1]:
+                        dev.copy_upper_to_host(h, t.data_ptr())
+                    else:
+                        dev.copy_to_host(h, t.data_ptr())
                     host.append(h)
                     d2h += h.nbytes
                 del host

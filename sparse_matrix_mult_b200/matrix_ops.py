@@ -112,6 +112,7 @@ class MatrixOpsLibrary:
         L.spgemm_b200_copy_to_host.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.spgemm_b200_copy_to_device.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.spgemm_b200_copy_on_device.argtypes = [_vp, _vp, ctypes.c_size_t]
+        L.spgemm_b200_copy_upper_to_host.argtypes = [_vp, _vp, ctypes.c_int]
         L.spgemm_b200_shared_alloc.argtypes = [ctypes.c_size_t]
         L.spgemm_b200_shared_alloc.restype = _vp
         L.spgemm_b200_shared_free.argtypes = [_vp]
