@@ -308,6 +308,8 @@ def run_ours(args, w, name, info, flops, rank, world):
             dev.triple_product(A, B, None, True, r0, r1, out=out)      # includes building H^T on the device
 
     small = (csr_bytes(a) + csr_bytes(b)) < (256 << 20)               # operands could sit in the 126 MB L2
+    if os.environ.get("SPGEMM_BENCH_NO_FLUSH"):                      # experiments only
+        small = False
     ms_c = ctypes_double()
 
     def barrier():
@@ -395,7 +397,8 @@ def run_ours(args, w, name, info, flops, rank, world):
             "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(info, parallelism=f"rows sharded over {world} GPU(s), flop-balanced",
-                           l2="flushed between timed steps (512 MB write)" if small else
+                           l2="flushed between timed steps (512 MB written, then 256 MB of it read back so L2 holds no "
+                              "dirty lines of the flush buffer)" if small else
                               "no flush: each step streams more bytes than the 126 MB L2"),
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
