@@ -157,10 +157,33 @@ k_scan_apply(const int32_t* __restrict__ in, OutT* __restrict__ out, int n, int 
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = (OutT)sums[nb];
 }
 
+// Small inputs: the whole scan in ONE block (each thread owns a contiguous chunk), one launch instead of three.
+template <typename OutT>
+__global__ void __launch_bounds__(1024)
+k_scan_small(const int32_t* __restrict__ in, OutT* __restrict__ out, int n) {
+    __shared__ long long red[33];
+    const int per = (n + 1023) / 1024;
+    const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+    long long s = 0;
+    for (int t = lo; t < hi; ++t) s += __ldg(in + t);
+    long long total;
+    long long run = block_excl_scan<long long>(s, red, &total);
+    for (int t = lo; t < hi; ++t) {
+        out[t] = (OutT)run;
+        run += __ldg(in + t);
+    }
+    if (threadIdx.x == 0) out[n] = (OutT)total;
+}
+
 template <typename OutT>
 static cudaError_t launch_scan(const LaunchCtx& lc, const int32_t* in, OutT* out, int n, int64_t* d_tmp) {
     if (n <= 0) {
         return cudaMemsetAsync(out, 0, sizeof(OutT), lc.stream);
+    }
+    if (n <= 32768) {
+        k_scan_small<OutT><<<1, 1024, 0, lc.stream>>>(in, out, n);
+        SB_LAUNCH_CHECK(lc);
+        return cudaSuccess;
     }
     int tile = (n + 1023) / 1024;
     tile = ((tile + 255) / 256) * 256;

@@ -47,6 +47,8 @@ struct Ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t aux[3] = {};
+    cudaEvent_t fork_ev = nullptr, join_ev[3] = {};
     cudaEvent_t ev[EV_COUNT] = {};
     bool ev_pending = false;
     unsigned ev_mask = 0;            // which events were recorded by the current call
@@ -87,7 +89,10 @@ int ensure_init() {
     return spgemm_b200_init(env ? atoi(env) : 0);
 }
 
-LaunchCtx lctx() { return LaunchCtx{g.stream, g.sm_count, &g.launches}; }
+LaunchCtx lctx() {
+    return LaunchCtx{g.stream, g.sm_count, &g.launches, {g.aux[0], g.aux[1], g.aux[2]}, g.fork_ev,
+                     {g.join_ev[0], g.join_ev[1], g.join_ev[2]}};
+}
 
 // kernel-variant overrides for experiments: SPGEMM_B200_DENSE_MODE / SPGEMM_B200_TRIPLE_MODE = 0 auto, 1 smem, 2 red
 int env_mode(const char* name) {
@@ -415,6 +420,11 @@ int spgemm_b200_init(int device) {
     CU(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
     for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&g.ev[i]));
+    for (int i = 0; i < 3; ++i) {
+        CU(cudaStreamCreateWithFlags(&g.aux[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&g.join_ev[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&g.fork_ev, cudaEventDisableTiming));
     CU(cudaHostAlloc(&g.h_small, 4096, cudaHostAllocDefault));
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -440,6 +450,8 @@ void spgemm_b200_shutdown(void) {
         g.host_cached = 0;
     }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(g.ev[i]);
+    for (int i = 0; i < 3; ++i) { cudaStreamDestroy(g.aux[i]); cudaEventDestroy(g.join_ev[i]); g.aux[i] = nullptr; }
+    cudaEventDestroy(g.fork_ev);
     cudaFreeHost(g.h_small);
     cudaStreamDestroy(g.own_stream);
     cudaMemPool_t pool;

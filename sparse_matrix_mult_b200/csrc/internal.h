@@ -19,6 +19,11 @@ struct LaunchCtx {
     cudaStream_t stream;
     int sm_count;
     int* launches;      // incremented once per kernel launch
+    // side streams for kernels of one phase that are independent of each other (the cost-bin kernels): on small
+    // inputs each of them is latency-bound with a handful of blocks, so they are run concurrently
+    cudaStream_t aux[3];
+    cudaEvent_t fork_ev;
+    cudaEvent_t join_ev[3];
 };
 
 // ---- analysis.cu --------------------------------------------------------------------------------

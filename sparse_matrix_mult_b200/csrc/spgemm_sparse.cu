@@ -350,6 +350,25 @@ cudaError_t sparse_kernels_configure() {
     return e;
 }
 
+// Run up to three independent bin kernels on side streams: fork after everything queued on the main stream so
+// far, join back before anything queued after.
+struct Fork {
+    const LaunchCtx& lc;
+    bool used[3] = {false, false, false};
+    bool forked = false;
+    explicit Fork(const LaunchCtx& l) : lc(l) {}
+    cudaStream_t side(int k, bool concurrent) {
+        if (!concurrent || lc.aux[k] == nullptr) return lc.stream;
+        if (!forked) { cudaEventRecord(lc.fork_ev, lc.stream); forked = true; }
+        if (!used[k]) { cudaStreamWaitEvent(lc.aux[k], lc.fork_ev, 0); used[k] = true; }
+        return lc.aux[k];
+    }
+    void join() {
+        for (int k = 0; k < 3; ++k)
+            if (used[k]) { cudaEventRecord(lc.join_ev[k], lc.aux[k]); cudaStreamWaitEvent(lc.stream, lc.join_ev[k], 0); }
+    }
+};
+
 static inline int grid_for(int items, int per_block, int cap) {
     int g = (items + per_block - 1) / per_block;
     if (g > cap) g = cap;
@@ -362,21 +381,25 @@ cudaError_t launch_symbolic(const LaunchCtx& lc, const SparseJob& job, const int
     const int up = job.upper_only ? 1 : 0;
     const size_t stride = (size_t)job.nrows;
     const int cap = lc.sm_count * 16;
+    const int nonempty = (h_counts[SYM_W64] != 0) + (h_counts[SYM_W256] != 0) + (h_counts[SYM_W1K] != 0) +
+                         (h_counts[SYM_BITMAP] != 0);
+    Fork fork(lc);
+    const bool conc = nonempty > 1;
     if (h_counts[SYM_W64]) {
         constexpr int W = 8;
-        k_symbolic_warp<64, W><<<grid_for(h_counts[SYM_W64], W, cap), W * 32, 0, lc.stream>>>(
+        k_symbolic_warp<64, W><<<grid_for(h_counts[SYM_W64], W, cap), W * 32, 0, fork.side(0, conc)>>>(
             job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + SYM_W64 * stride, h_counts[SYM_W64], d_nnz);
         SB_LAUNCH_CHECK(lc);
     }
     if (h_counts[SYM_W256]) {
         constexpr int W = 8;
-        k_symbolic_warp<256, W><<<grid_for(h_counts[SYM_W256], W, cap), W * 32, 0, lc.stream>>>(
+        k_symbolic_warp<256, W><<<grid_for(h_counts[SYM_W256], W, cap), W * 32, 0, fork.side(1, conc)>>>(
             job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + SYM_W256 * stride, h_counts[SYM_W256], d_nnz);
         SB_LAUNCH_CHECK(lc);
     }
     if (h_counts[SYM_W1K]) {
         constexpr int W = 8;
-        k_symbolic_warp<1024, W><<<grid_for(h_counts[SYM_W1K], W, cap), W * 32, 0, lc.stream>>>(
+        k_symbolic_warp<1024, W><<<grid_for(h_counts[SYM_W1K], W, cap), W * 32, 0, fork.side(2, conc)>>>(
             job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + SYM_W1K * stride, h_counts[SYM_W1K], d_nnz);
         SB_LAUNCH_CHECK(lc);
     }
@@ -404,6 +427,7 @@ cudaError_t launch_symbolic(const LaunchCtx& lc, const SparseJob& job, const int
                 (int)window_bits, d_nnz, d_work_counter);
         SB_LAUNCH_CHECK(lc);
     }
+    fork.join();
     return cudaSuccess;
 }
 
@@ -412,23 +436,27 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
     const int up = job.upper_only ? 1 : 0;
     const size_t stride = (size_t)job.nrows;
     const int cap = lc.sm_count * 16;
+    const int nonempty = (h_counts[NUM_W64] != 0) + (h_counts[NUM_W256] != 0) + (h_counts[NUM_W1K] != 0) +
+                         (h_counts[NUM_RANK] != 0);
+    Fork fork(lc);
+    const bool conc = nonempty > 1;
     if (h_counts[NUM_W64]) {
         constexpr int W = 8;
-        k_numeric_warp<64, W><<<grid_for(h_counts[NUM_W64], W, cap), W * 32, 0, lc.stream>>>(
+        k_numeric_warp<64, W><<<grid_for(h_counts[NUM_W64], W, cap), W * 32, 0, fork.side(0, conc)>>>(
             job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_W64 * stride, h_counts[NUM_W64], c_ptr,
             c_idx, c_val);
         SB_LAUNCH_CHECK(lc);
     }
     if (h_counts[NUM_W256]) {
         constexpr int W = 8;
-        k_numeric_warp<256, W><<<grid_for(h_counts[NUM_W256], W, cap), W * 32, 0, lc.stream>>>(
+        k_numeric_warp<256, W><<<grid_for(h_counts[NUM_W256], W, cap), W * 32, 0, fork.side(1, conc)>>>(
             job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_W256 * stride, h_counts[NUM_W256], c_ptr,
             c_idx, c_val);
         SB_LAUNCH_CHECK(lc);
     }
     if (h_counts[NUM_W1K]) {
         constexpr int W = 4;
-        k_numeric_warp<1024, W><<<grid_for(h_counts[NUM_W1K], W, cap), W * 32, 0, lc.stream>>>(
+        k_numeric_warp<1024, W><<<grid_for(h_counts[NUM_W1K], W, cap), W * 32, 0, fork.side(2, conc)>>>(
             job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_W1K * stride, h_counts[NUM_W1K], c_ptr,
             c_idx, c_val);
         SB_LAUNCH_CHECK(lc);
@@ -462,6 +490,7 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
         }
         SB_LAUNCH_CHECK(lc);
     }
+    fork.join();
     return cudaSuccess;
 }
 
