@@ -489,11 +489,12 @@ void* spgemm_b200_host_alloc(size_t bytes) {
     const size_t size = ((bytes ? bytes : 1) + granule - 1) / granule * granule;
     {
         std::lock_guard<std::mutex> hl(g.host_mu);
-        auto it = g.host_free.find(size);
-        if (it != g.host_free.end()) {
+        // smallest cached buffer that fits, as long as it wastes less than half of itself
+        auto it = g.host_free.lower_bound(size);
+        if (it != g.host_free.end() && it->first <= 2 * size) {
             void* p = it->second;
+            g.host_cached -= it->first;
             g.host_free.erase(it);
-            g.host_cached -= size;
             return p;
         }
     }
