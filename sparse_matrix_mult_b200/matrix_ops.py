@@ -186,6 +186,9 @@ def _result_array(shape, dtype):
 def csr_to_arrays(csr):
     """(indptr int32, indices int32, data float64) contiguous views/copies of a scipy CSR, cast exactly like
     csr_to_sparsemat (matrix_ops.py:187-202); no canonicalisation."""
+    if csr.nnz >= 2 ** 31 or max(csr.shape) >= 2 ** 31:
+        raise OverflowError("operands with nnz or a dimension >= 2**31 do not fit the int32 CSR of this interface "
+                            "(the reference has the same limit: include/matrix_def.h:21-22, matrix_ops.py:196-197)")
     return (np.ascontiguousarray(csr.indptr, dtype=np.int32),
             np.ascontiguousarray(csr.indices, dtype=np.int32),
             np.ascontiguousarray(csr.data, dtype=np.float64))
