@@ -66,5 +66,8 @@ if multi:
     for d in multi:
         e = d.get("e2e") or {}
         out.append(f"| {d['config']['workload']} | {d['n_gpus']} | {d['ms_per_step']:.3f} | {d['value']:.1f} | {e.get('ms_per_step') and round(e['ms_per_step'], 1)} |")
+notes = os.path.join(dst, "multi_gpu_notes.md")
+if os.path.exists(notes):
+    out += ["", open(notes).read().rstrip()]
 open(os.path.join(dst, "SUMMARY.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
