@@ -213,7 +213,8 @@ SPGEMM_B200_API int   spgemm_b200_ipc_export(const void *d_ptr, unsigned char *h
 SPGEMM_B200_API int   spgemm_b200_ipc_open(const unsigned char *handle /* 64 bytes */, void **d_ptr);
 SPGEMM_B200_API int   spgemm_b200_ipc_close(void *d_ptr);
 
-/* Make the library launch on `stream` (a cudaStream_t; NULL restores the library's own stream). */
+/* Make the library launch on `stream` (a cudaStream_t; NULL restores the library's own stream; pass
+   cudaStreamLegacy, i.e. (cudaStream_t)0x1, to name the legacy default stream). */
 SPGEMM_B200_API int spgemm_b200_set_stream(void *stream);
 
 /* CUDA-event stopwatch on the library stream: start records an event, stop records another, waits for it and

@@ -19,9 +19,20 @@ def init(device=0):
     _check(matrix_ops.get_lib().spgemm_b200_init(int(device)), "spgemm_b200_init")
 
 
+CUDA_STREAM_LEGACY = 1      # cudaStreamLegacy: the handle that names the legacy default stream explicitly
+
+
 def set_stream(stream_ptr):
-    """Launch on a caller stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None restores the own stream."""
-    _check(matrix_ops.get_lib().spgemm_b200_set_stream(_vp(stream_ptr or 0)), "spgemm_b200_set_stream")
+    """Launch on a caller stream; None restores the library's own stream.
+
+    torch.cuda.current_stream().cuda_stream is 0 for torch's default stream -- the LEGACY default stream.  0 is also
+    how the C ABI spells "use your own stream", so 0 is translated to cudaStreamLegacy here: the library then
+    really runs on torch's stream and is ordered with the NCCL collectives torch issues around it."""
+    if stream_ptr is None:
+        handle = 0
+    else:
+        handle = int(stream_ptr) or CUDA_STREAM_LEGACY
+    _check(matrix_ops.get_lib().spgemm_b200_set_stream(_vp(handle)), "spgemm_b200_set_stream")
 
 
 def copy_on_device(dst_ptr, src_ptr, nbytes):

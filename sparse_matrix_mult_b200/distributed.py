@@ -189,16 +189,21 @@ def cuda_compute_block(kind, upper_only):
     from . import device as dev
 
     def run(a_t, b_t, r0, r1):
+        # same stream as torch (ordered with the broadcasts before and the gather after) -- and, belt and braces,
+        # a host-side wait on both ends: the operands must have landed, the block must be complete
+        torch.cuda.current_stream().synchronize()
         dev.set_stream(torch.cuda.current_stream().cuda_stream)
         (ash, ap, ai, av), (bsh, bp, bi, bv) = a_t, b_t
         A, B = _wrap(dev, a_t), _wrap(dev, b_t)
         if kind == "dense":
             out = torch.empty((r1 - r0, bsh[1]), dtype=torch.float64, device=ap.device)
             dev.spgemm_dense(A, B, upper_only, r0, r1, out=out.data_ptr())
+            dev.synchronize()
             return out
         if kind == "triple":
             out = torch.empty((r1 - r0, ash[0]), dtype=torch.float64, device=ap.device)
             dev.triple_product(A, B, None, upper_only, r0, r1, out=out.data_ptr())
+            dev.synchronize()
             return out
         res = dev.spgemm_csr(A, B, upper_only, r0, r1)
         p, i, v = res.device_ptrs()
@@ -225,6 +230,7 @@ def cuda_partition(a_t, b_t, kind, upper_only, world):
     """Flop-balanced bounds from the GPU cost pass (spgemm_b200_row_costs + spgemm_b200_partition)."""
     from . import device as dev
     from .matrix_ops import matrix_ops
+    torch.cuda.current_stream().synchronize()            # the broadcast operands have landed
     dev.set_stream(torch.cuda.current_stream().cuda_stream)
     A, B = _wrap(dev, a_t), _wrap(dev, b_t)
     if kind == "triple":
@@ -270,6 +276,7 @@ def multiply_sharded_peer(matrix_a, matrix_b, kind, upper_only, device):
     buf = _peer_cache[key]
     bounds = cuda_partition(a_t, b_t, kind, upper_only, world)
     r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    torch.cuda.current_stream().synchronize()
     dev.set_stream(torch.cuda.current_stream().cuda_stream)
     A, B = _wrap(dev, a_t), _wrap(dev, b_t)
     if r1 > r0:
