@@ -28,16 +28,6 @@ __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
-template <typename T>
-__device__ __forceinline__ T warp_max(T v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        T w = __shfl_xor_sync(FULL, v, o);
-        v = w > v ? w : v;
-    }
-    return v;
-}
-
 // inclusive warp prefix sum
 template <typename T>
 __device__ __forceinline__ T warp_incl_scan(T v) {
@@ -80,12 +70,6 @@ __device__ __forceinline__ void st_stream_f64x2(double* p, double a, double b) {
 __device__ __forceinline__ void st_stream_f64(double* p, double a) {
     asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(a) : "memory");
 }
-__device__ __forceinline__ void st_stream_i32(int32_t* p, int32_t a) {
-    asm volatile("st.global.cs.s32 [%0], %1;" ::"l"(p), "r"(a) : "memory");
-}
-// 128-bit read-only loads
-__device__ __forceinline__ int4 ld_i32x4(const int32_t* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
-__device__ __forceinline__ double2 ld_f64x2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 // ---------------------------------------------------------------------------------------------------
 // hashing: multiplicative hash reduced to [0, size) without a modulo (size need not be a power of two)
@@ -190,21 +174,13 @@ struct SegScratch {
     int red[33];
 };
 
-struct NoHook {
-    __device__ __forceinline__ void operator()() const {}
-};
-
-// `hook` runs once, after the first batch of extent loads has been issued and before their values are
-// consumed: independent work placed there overlaps the gather latency.
-template <bool WITH_VALUES, int MAXT, class F, class H = NoHook>
+template <bool WITH_VALUES, int MAXT, class F>
 __device__ __forceinline__ void expand_row_block(const Csr& A, const Csr& B, int a_begin, int a_end,
                                                  int col_lo, int col_hi, bool windowed, bool b_sorted,
-                                                 SegScratch<MAXT>& sc, F&& f, H&& hook = NoHook(),
-                                                 int clip_min = kClipMin) {
+                                                 SegScratch<MAXT>& sc, F&& f) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     const bool filter = windowed;
-    bool first = true;
     for (int base = a_begin; base < a_end; base += nt) {
         const int p = base + tid;
         int s = 0, len = 0;
@@ -219,9 +195,8 @@ __device__ __forceinline__ void expand_row_block(const Csr& A, const Csr& B, int
             s = __ldg(B.ptr + j);
             e = __ldg(B.ptr + j + 1);
         }
-        if (first) { hook(); first = false; }
         if (j >= 0) {
-            if (windowed && b_sorted && e - s > clip_min) {
+            if (windowed && b_sorted && e - s > kClipMin) {
                 if (__ldg(B.idx + s) < col_lo) s = lower_bound(B.idx, s, e, col_lo);
                 if (e > s && __ldg(B.idx + e - 1) >= col_hi) e = lower_bound(B.idx, s, e, col_hi);
             }
@@ -279,7 +254,6 @@ __device__ __forceinline__ void expand_row_block(const Csr& A, const Csr& B, int
             __syncthreads();
         }
     }
-    if (first) hook();
 }
 
 }  // namespace sb
