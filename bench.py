@@ -419,6 +419,19 @@ def run_ours(args, w, name, info, flops, rank, world):
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": cflops / dt / 1e9, "unit": UNIT, "cores": cores, "kind": ckind,
                                 "sample": desc, "seconds": dt}
+        if kind == "sparse":
+            # the reference has no working multi-threaded sparse path; for scale, the oracle's
+            # OpenMP port of it (bit-identical rows, dynamic row blocks) on every host core
+            from oracle import port
+            ncores = os.cpu_count() or 1
+            sub = a if "full" in desc else a[:int(desc.split("[0,")[1].split(")")[0])]
+            port.spgemm_csr(sub, b, sym, omp_blocks=16 * ncores, copy=False)          # warm-up (threads, pages)
+            t0 = time.perf_counter()
+            port.spgemm_csr(sub, b, sym, omp_blocks=16 * ncores, copy=False)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline_omp_port"] = {"value": cflops / dt / 1e9, "unit": UNIT, "cores": ncores, "kind": "port",
+                                             "sample": desc.split(":")[0] + ": oracle_spgemm_csr_omp, C call only",
+                                             "seconds": dt}
     emit(line)
 
 

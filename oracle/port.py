@@ -40,6 +40,8 @@ def lib():
         csr_args = [ctypes.c_int] * 3 + [_i32p, _i32p, _f64p] * 2
         L.oracle_spgemm_csr.argtypes = csr_args + [ctypes.c_int]
         L.oracle_spgemm_csr.restype = ctypes.POINTER(_OracleCsr)
+        L.oracle_spgemm_csr_omp.argtypes = csr_args + [ctypes.c_int, ctypes.c_int]
+        L.oracle_spgemm_csr_omp.restype = ctypes.POINTER(_OracleCsr)
         L.oracle_csr_free.argtypes = [ctypes.POINTER(_OracleCsr)]
         L.oracle_csr_free.restype = None
         L.oracle_spgemm_dense.argtypes = csr_args + [ctypes.c_int, _f64p]
@@ -67,14 +69,24 @@ def _p(a, t):
     return a.ctypes.data_as(t)
 
 
-def spgemm_csr(a, b, upper_only=False):
-    """A*B as csr_matrix, columns in first-touch order, int64 indptr when nnz >= 2**31 else int32."""
+def spgemm_csr(a, b, upper_only=False, omp_blocks=0, copy=True):
+    """A*B as csr_matrix, columns in first-touch order, int64 indptr when nnz >= 2**31 else int32.
+    omp_blocks > 0 runs the multi-threaded variant (OpenMP, that many row blocks, dynamic schedule) -- the
+    many-core CPU baseline of bench.py; the result is bit-identical.  copy=False only times the C call."""
     (m, k), ap, ai, av = _csr_arrays(a)
     (k2, n), bp, bi, bv = _csr_arrays(b)
     assert k == k2
     L = lib()
-    h = L.oracle_spgemm_csr(m, k, n, _p(ap, _i32p), _p(ai, _i32p), _p(av, _f64p),
-                            _p(bp, _i32p), _p(bi, _i32p), _p(bv, _f64p), int(bool(upper_only)))
+    if omp_blocks > 0:
+        h = L.oracle_spgemm_csr_omp(m, k, n, _p(ap, _i32p), _p(ai, _i32p), _p(av, _f64p),
+                                    _p(bp, _i32p), _p(bi, _i32p), _p(bv, _f64p), int(bool(upper_only)),
+                                    int(omp_blocks))
+    else:
+        h = L.oracle_spgemm_csr(m, k, n, _p(ap, _i32p), _p(ai, _i32p), _p(av, _f64p),
+                                _p(bp, _i32p), _p(bi, _i32p), _p(bv, _f64p), int(bool(upper_only)))
+    if h and not copy:
+        L.oracle_csr_free(h)
+        return None
     if not h:
         raise MemoryError("oracle_spgemm_csr")
     try:

@@ -111,6 +111,102 @@ oracle_csr *oracle_spgemm_csr(int m, int k, int n,
 }
 
 /*
+ * Multi-threaded variant of oracle_spgemm_csr for the CPU baseline of bench.py only ("port", many cores): the
+ * reference's design -- contiguous row blocks per OpenMP thread, private result buffers, serial stitch
+ * (src/sparse_sparse_sparse.cpp:188-197, 228-249, 265-291) -- restated so that it works (today's src/ does not,
+ * SURVEY.md 0.3).  Rows are computed exactly as in the serial routine, so the result is bit-identical to it
+ * (tests/test_oracle.py).  Blocks are many and handed out dynamically: power-law inputs unbalance an even split.
+ * Compiled without OpenMP this is the serial routine over one block.
+ */
+oracle_csr *oracle_spgemm_csr_omp(int m, int k, int n,
+                                  const int32_t *a_ptr, const int32_t *a_idx, const double *a_val,
+                                  const int32_t *b_ptr, const int32_t *b_idx, const double *b_val,
+                                  int upper_only, int blocks)
+{
+    (void)k;
+    if (blocks < 1) blocks = 1;
+    if (blocks > m) blocks = m > 0 ? m : 1;
+    oracle_csr *c = (oracle_csr *)calloc(1, sizeof *c);
+    if (!c) return NULL;
+    c->rows = m;
+    c->indptr = (int64_t *)calloc((size_t)m + 1, sizeof(int64_t));
+    int32_t **part_idx = (int32_t **)calloc((size_t)blocks, sizeof *part_idx);
+    double **part_val = (double **)calloc((size_t)blocks, sizeof *part_val);
+    int64_t *part_nnz = (int64_t *)calloc((size_t)blocks, sizeof *part_nnz);
+    int failed = !c->indptr || !part_idx || !part_val || !part_nnz;
+#ifdef _OPENMP
+#pragma omp parallel if (!failed)
+#endif
+    {
+        int64_t *where = failed ? NULL : (int64_t *)malloc(((size_t)n + 1) * sizeof(int64_t));
+        if (where) for (int j = 0; j < n; ++j) where[j] = -1;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+        for (int blk = 0; blk < blocks; ++blk) {
+            if (!where) { failed = 1; continue; }
+            const int r0 = (int)((int64_t)m * blk / blocks), r1 = (int)((int64_t)m * (blk + 1) / blocks);
+            int64_t cap = 1024, fill = 0;
+            int32_t *ci = (int32_t *)malloc((size_t)cap * sizeof(int32_t));
+            double *cv = (double *)malloc((size_t)cap * sizeof(double));
+            /* positions are block-local: offset them so that stale marks of earlier blocks never look fresh */
+            for (int i = r0; i < r1 && ci && cv; ++i) {
+                const int64_t row_begin = fill;
+                for (int32_t p = a_ptr[i]; p < a_ptr[i + 1]; ++p) {
+                    const double av = a_val[p];
+                    const int32_t j = a_idx[p];
+                    for (int32_t q = b_ptr[j]; q < b_ptr[j + 1]; ++q) {
+                        const int32_t col = b_idx[q];
+                        if (upper_only && col < i) continue;
+                        if (where[col] >= row_begin && where[col] < fill && ci[where[col]] == col) {
+                            cv[where[col]] += av * b_val[q];
+                        } else {
+                            if (fill == cap) {
+                                cap *= 2;
+                                int32_t *ni = (int32_t *)realloc(ci, (size_t)cap * sizeof(int32_t));
+                                double *nv = (double *)realloc(cv, (size_t)cap * sizeof(double));
+                                if (!ni || !nv) { if (ni) ci = ni; if (nv) cv = nv; failed = 1; break; }
+                                ci = ni; cv = nv;
+                            }
+                            ci[fill] = col;
+                            cv[fill] = av * b_val[q];
+                            where[col] = fill;
+                            ++fill;
+                        }
+                    }
+                }
+                c->indptr[i + 1] = fill - row_begin;          /* per-row count, prefix-summed below */
+            }
+            if (!ci || !cv) failed = 1;
+            part_idx[blk] = ci; part_val[blk] = cv; part_nnz[blk] = fill;
+        }
+        free(where);
+    }
+    if (!failed) {
+        for (int i = 0; i < m; ++i) c->indptr[i + 1] += c->indptr[i];
+        c->nnz = c->indptr[m];
+        c->indices = (int32_t *)malloc((size_t)(c->nnz ? c->nnz : 1) * sizeof(int32_t));
+        c->values = (double *)malloc((size_t)(c->nnz ? c->nnz : 1) * sizeof(double));
+        failed = !c->indices || !c->values;
+    }
+    if (!failed) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+        for (int blk = 0; blk < blocks; ++blk) {
+            const int r0 = (int)((int64_t)m * blk / blocks);
+            memcpy(c->indices + c->indptr[r0], part_idx[blk], (size_t)part_nnz[blk] * sizeof(int32_t));
+            memcpy(c->values + c->indptr[r0], part_val[blk], (size_t)part_nnz[blk] * sizeof(double));
+        }
+    }
+    if (part_idx) for (int b = 0; b < blocks; ++b) free(part_idx[b]);
+    if (part_val) for (int b = 0; b < blocks; ++b) free(part_val[b]);
+    free(part_idx); free(part_val); free(part_nnz);
+    if (failed) { oracle_csr_free(c); return NULL; }
+    return c;
+}
+
+/*
  * Dense C (m x n, row-major, caller-allocated, overwritten) = A*B.
  * Follows src/sparse_sparse_dense.cpp:108-130 (dense_nosym) and :40-73
  * (dense_sym, `i <= col` filter at :59; the lower triangle stays 0 because the

@@ -86,3 +86,21 @@ def test_oracle_matches_reference_binaries():
         t = port.triple_product(h, q, full)
         assert np.array_equal(t, ref.shipped().triple(h, q, full))
         np.testing.assert_allclose(t, ref.omp().triple(h, q, full), rtol=1e-13, atol=1e-15)
+
+
+def test_openmp_port_is_bit_identical_to_the_serial_port():
+    """The many-core CPU baseline of bench.py (oracle_spgemm_csr_omp) computes every row exactly like the serial
+    restatement, whatever the number of row blocks."""
+    from sparse_matrix_mult_b200 import synthetic
+    a = synthetic.rmat(11)
+    for upper in (False, True):
+        want = port.spgemm_csr(a, a, upper)
+        for blocks in (1, 3, 64, 5000):
+            got = port.spgemm_csr(a, a, upper, omp_blocks=blocks)
+            assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+            assert np.array_equal(got.data, want.data)
+    rng = np.random.default_rng(2)
+    x = sp.random(37, 53, density=0.2, format='csr', random_state=rng)
+    y = sp.random(53, 41, density=0.2, format='csr', random_state=rng)
+    got, want = port.spgemm_csr(x, y, omp_blocks=8), port.spgemm_csr(x, y)
+    assert np.array_equal(got.indices, want.indices) and np.array_equal(got.data, want.data)
