@@ -323,21 +323,24 @@ def run_ours(args, w, name, info, flops, rank, world):
         step_device()
     barrier()
     kernel_ms, step_ms, launches, bytes_min, last_stats = [], [], 0, 0, {}
-    with ClockSampler(local) as clocks:
-        for _ in range(args.steps):
-            if small:
-                lib.spgemm_b200_flush_l2()
-            barrier()
-            lib.spgemm_b200_timer_start()
-            step_device()
-            lib.spgemm_b200_timer_stop(ms_c)
-            step_ms.append(ms_c.value)
-            st = dev.last_stats()
-            last_stats = st
-            kernel_ms.append(st["ms_numeric"])
-            launches += st["launches"]
-            bytes_min = st["bytes_min"]
+    # clocks / throttle reasons are sampled from here to the end of the end-to-end leg (the resident leg alone
+    # lasts a few milliseconds: too short for nvidia-smi's sampling period)
+    clocks = ClockSampler(local)
+    clocks.__enter__()
+    for _ in range(args.steps):
+        if small:
+            lib.spgemm_b200_flush_l2()
         barrier()
+        lib.spgemm_b200_timer_start()
+        step_device()
+        lib.spgemm_b200_timer_stop(ms_c)
+        step_ms.append(ms_c.value)
+        st = dev.last_stats()
+        last_stats = st
+        kernel_ms.append(st["ms_numeric"])
+        launches += st["launches"]
+        bytes_min = st["bytes_min"]
+    barrier()
     t_local = float(np.sum(step_ms))
     if dist:
         import torch
@@ -386,6 +389,7 @@ def run_ours(args, w, name, info, flops, rank, world):
         from sparse_matrix_mult_b200 import distributed as sd
         e2e = sd.bench_e2e(args, w, flops, rank, world, csr_bytes)
 
+    clocks.__exit__(None, None, None)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -410,7 +414,7 @@ def run_ours(args, w, name, info, flops, rank, world):
             "phases_ms": {k: round(last_stats.get(k, 0.0), 4) for k in
                           ("ms_analysis", "ms_symbolic", "ms_numeric", "ms_post")},
             "nnz_c": int(last_stats.get("nnz_c", 0)),
-            "clocks": clocks.summary()}
+            "clocks": dict(clocks.summary(), window="timed steps of the resident leg + the end-to-end leg")}
     # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------
     if world == 1 and not args.no_cpu:
         fn, cflops, ckind, cores, desc = cpu_sample(w, name)
