@@ -323,8 +323,10 @@ cudaError_t launch_narrow_indptr(const LaunchCtx& lc, const int64_t* in, int32_t
 // Cost of row i of the triple product H Q H^T for the flop-balanced multi-GPU split:
 //   P1_i = sum over (i,j) in H of nnz(Q[j,:])                         (expansion of H[i,:] Q)
 //   P2_i = sum over those (j,c) of nnz(H^T[c,:])                      (contraction against H^T), scaled by the
-//          fraction (n - i) / n of columns kept when only the upper triangle is computed; every product also
-//          pays one look at its row of H^T, hence 2 * P1.
+//          fraction (n - i) / n of columns kept when only the upper triangle is computed.
+// cost_i = 7 * P1_i + P2_i: every product of the expansion pays its gathers of Q and of the extent of its row of H^T
+// whether or not any entry survives the k >= i cut; fitted to the per-rank kernel times of cfg 5 on four B200s
+// (t(x) ~ 15.4 + 17.3 (1 - x) per unit of rows at relative position x, i.e. one product ~ 7 visited entries).
 // One warp per row.
 __global__ void __launch_bounds__(256)
 k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, int64_t* __restrict__ costs) {
@@ -340,7 +342,7 @@ k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, int64_t* __restrict__ costs
     p2 = warp_sum(p2);
     if (lane_id() == 0) {
         if (upper_only) p2 = (long long)((double)p2 * (double)(H.rows - row) / (double)H.rows);
-        costs[row] = 2 * p1 + p2;
+        costs[row] = 7 * p1 + p2;
     }
 }
 cudaError_t launch_triple_costs(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool upper_only,

@@ -39,7 +39,7 @@ def partition_by_cost(costs, parts):
 
 def host_row_costs(a, b, kind, upper_only):
     """Per-row cost on the host (numpy): products of A rows against B; for the triple product
-    P1_i + P2_i * (n - i)/n, the same model as k_triple_costs (csrc/analysis.cu)."""
+    7 P1_i + P2_i * (n - i)/n, the same model as k_triple_costs (csrc/analysis.cu)."""
     blen = np.diff(b.indptr).astype(np.int64)
     rows = np.repeat(np.arange(a.shape[0]), np.diff(a.indptr))
     p1 = np.bincount(rows, weights=blen[a.indices], minlength=a.shape[0]).astype(np.float64)
@@ -53,7 +53,7 @@ def host_row_costs(a, b, kind, upper_only):
     if upper_only:
         n = a.shape[0]
         p2 = p2 * (n - np.arange(n)) / max(1, n)
-    return p1 + p2
+    return 7.0 * p1 + p2
 
 
 # ------------------------------------------------------------------------------------------------------
