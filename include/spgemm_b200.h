@@ -45,8 +45,20 @@ extern "C" {
 /* Opaque handles. */
 typedef struct spgemm_b200_mat spgemm_b200_mat;        /* a CSR matrix resident in HBM            */
 typedef struct spgemm_b200_result spgemm_b200_result;  /* a sparse product C resident in HBM      */
+typedef struct spgemm_b200_multi_result spgemm_b200_multi_result;  /* a sparse product in row blocks on N GPUs */
 
-/* Per-call timing/size record of the LAST compute call on this thread's context.
+/* Thread safety.  The library keeps per-call state (stats, staging buffers) in one context per CUDA device.
+   Every entry point locks the context it works on for its whole duration and makes that context's device
+   current for the call (the caller's current device is restored on return), so:
+     - concurrent calls from several threads are safe; calls on the same device are serialised;
+     - handles may be used from any thread; a handle remembers its device;
+     - spgemm_b200_get_stats / _last_error describe the last call OF THE CALLING THREAD only if no other thread
+       called in between (stats are per device, the error string is per thread);
+     - spgemm_b200_shutdown must not run concurrently with other calls.
+   (The reference C library is stateless: every call allocates and frees its own scratch,
+   src/sparse_sparse_sparse.cpp:199-291.) */
+
+/* Per-call timing/size record of the LAST compute call on the default device's context.
    All times are CUDA-event milliseconds on the library stream. */
 typedef struct {
     double  ms_h2d;        /* host -> device copies of the operands                                   */
@@ -82,8 +94,16 @@ SPGEMM_B200_API int spgemm_b200_device_count(void);
    OpenMP team setup (omp_get_max_threads(), src/sparse_sparse_sparse.cpp:188-197). */
 SPGEMM_B200_API int spgemm_b200_init(int device);
 
-/* Release every cached device/pinned buffer and the stream. */
+/* Release every cached device/pinned buffer and the streams of every device context. */
 SPGEMM_B200_API void spgemm_b200_shutdown(void);
+
+/* Give cached memory back: the library allocates from a PRIVATE stream-ordered pool per device (the device's
+   default pool, which other libraries share, is never reconfigured) that keeps up to SPGEMM_B200_POOL_KEEP_GB
+   (default 32) of freed workspaces for reuse, and caches the pinned buffers of the most recent results
+   (SPGEMM_B200_PINNED_CACHE_GB, default 4, or the last result alone when it is larger).  This call trims
+   every pool to `keep_bytes` and drops the pinned cache.  Replaces the free() calls of destroy_sparsemat /
+   destroy_darray (src/memfunctions.cpp:22-65) as the point where memory returns to the system. */
+SPGEMM_B200_API int spgemm_b200_trim(size_t keep_bytes);
 
 /* Timing/size record of the last compute call. */
 SPGEMM_B200_API int spgemm_b200_get_stats(spgemm_b200_stats *out);
@@ -150,8 +170,17 @@ SPGEMM_B200_API int spgemm_b200_mat_wrap(int rows, int cols, int64_t nnz,
                          const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
                          spgemm_b200_mat **out);
 
-/* Build the CSR of X^T on the device. */
+/* Build the CSR of X^T on the device; every row of the result is sorted by DESCENDING column (what the
+   triple product's upper-triangle contraction wants). */
 SPGEMM_B200_API int spgemm_b200_mat_transpose(const spgemm_b200_mat *x, spgemm_b200_mat **out);
+
+/* Device-side canonicalisation (the reference coerces on the host,
+   sparse_matrix_mult/matrix_ops.py:307-310): sort every row of x by ascending column (duplicates stay; the
+   accumulators sum them).  In place for matrices the library uploaded; borrowed (wrapped) arrays are left
+   alone and a sorted shadow copy is cached on the handle.  The compute entry points do this automatically for
+   an unsorted right operand.  spgemm_b200_mat_is_sorted: 1 / 0, or -1 on error (runs the validation pass). */
+SPGEMM_B200_API int spgemm_b200_mat_sort(spgemm_b200_mat *x);
+SPGEMM_B200_API int spgemm_b200_mat_is_sorted(const spgemm_b200_mat *x);
 
 SPGEMM_B200_API void spgemm_b200_mat_free(spgemm_b200_mat *m);
 
@@ -212,6 +241,34 @@ SPGEMM_B200_API void  spgemm_b200_shared_free(void *d_ptr);
 SPGEMM_B200_API int   spgemm_b200_ipc_export(const void *d_ptr, unsigned char *handle /* 64 bytes */);
 SPGEMM_B200_API int   spgemm_b200_ipc_open(const unsigned char *handle /* 64 bytes */, void **d_ptr);
 SPGEMM_B200_API int   spgemm_b200_ipc_close(void *d_ptr);
+
+/* ---- single-process multi-GPU (N GPUs behind one call) --------------------------------------------------
+   The reference sizes its OpenMP team inside the call (src/sparse_sparse_sparse.cpp:188-197) and hands every
+   thread a row range from limits() (src/workdivision.cpp:16-89).  Here: one host thread per GPU inside the call
+   (devices 0..n_gpus-1), rows split by the flop-balanced partition, every GPU loads the operands over its own
+   PCIe link and writes its row block straight into the caller's host result (symmetric dense modes: upper
+   trapezoids only).  Same argument meaning as spgemm_b200_dense / _triple (upper mode) / _csr. */
+SPGEMM_B200_API int spgemm_b200_multi_dense(int n_gpus, int m, int k, int n,
+                            const int32_t *a_indptr, const int32_t *a_indices, const double *a_values,
+                            const int32_t *b_indptr, const int32_t *b_indices, const double *b_values,
+                            int upper_only, double *c_host);
+SPGEMM_B200_API int spgemm_b200_multi_triple(int n_gpus, int n, int k,
+                             const int32_t *h_indptr, const int32_t *h_indices, const double *h_values,
+                             const int32_t *q_indptr, const int32_t *q_indices, const double *q_values,
+                             double *c_host);
+SPGEMM_B200_API int spgemm_b200_multi_csr(int n_gpus, int m, int k, int n,
+                          const int32_t *a_indptr, const int32_t *a_indices, const double *a_values,
+                          const int32_t *b_indptr, const int32_t *b_indices, const double *b_values,
+                          int upper_only, spgemm_b200_multi_result **out);
+SPGEMM_B200_API int64_t spgemm_b200_multi_result_nnz(const spgemm_b200_multi_result *r);
+/* every GPU copies its block to its final offset of the caller's arrays (parallel stitch; replaces
+   src/sparse_sparse_sparse.cpp:265-291) */
+SPGEMM_B200_API int  spgemm_b200_multi_result_copy(const spgemm_b200_multi_result *r, void *indptr, int index64,
+                                   int32_t *indices, double *values);
+SPGEMM_B200_API void spgemm_b200_multi_result_free(spgemm_b200_multi_result *r);
+/* diagnostics of the last multi-GPU call: the row bounds (returns their count, n_gpus + 1) and the per-GPU stats */
+SPGEMM_B200_API int spgemm_b200_multi_last_bounds(int32_t *bounds, int capacity);
+SPGEMM_B200_API int spgemm_b200_multi_last_stats(int part, spgemm_b200_stats *out);
 
 /* Make the library launch on `stream` (a cudaStream_t; NULL restores the library's own stream; pass
    cudaStreamLegacy, i.e. (cudaStream_t)0x1, to name the legacy default stream). */

@@ -78,39 +78,50 @@ cudaError_t launch_row_products(const LaunchCtx& lc, const Csr& A, const Csr& B,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Sortedness: a CSR has sorted rows iff every descent idx[q] > idx[q+1] sits on a row boundary.
-// counts[0] = descents anywhere, counts[1] = descents on row boundaries.
+// Validation + sortedness of a CSR in one pass over idx and ptr (an out-of-range index would become an
+// out-of-bounds device atomic).  A CSR has sorted rows iff every descent idx[q] > idx[q+1] sits on a row boundary.
+// flags[1] = descents anywhere, flags[2] = descents on row boundaries, flags[3] = invalid entries (column index
+// outside [0, cols), indptr not monotone / outside [0, nnz], indptr[0] != 0, indptr[rows] != nnz);
+// flags[0] = rows sorted (set by k_sorted_flag).
 __global__ void __launch_bounds__(256)
-k_count_descents(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, int rows, int64_t nnz,
-                 int32_t* __restrict__ counts) {
+k_check_csr(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, int rows, int cols, int64_t nnz,
+            int32_t* __restrict__ flags) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int any = 0, edge = 0;
-    if (t + 1 < nnz) any = __ldg(idx + t) > __ldg(idx + t + 1);
+    int any = 0, edge = 0, bad = 0;
+    if (t < nnz) {
+        const int c = __ldg(idx + t);
+        bad = c < 0 || c >= cols;
+        if (t + 1 < nnz) any = c > __ldg(idx + t + 1);
+    }
     if (t < rows) {
         const int s = __ldg(ptr + t), e = __ldg(ptr + t + 1);
-        if (e > s && e < nnz) edge = __ldg(idx + e - 1) > __ldg(idx + e);
+        if (s < 0 || e < s || (int64_t)e > nnz) bad = 1;
+        else if (e > s && e < nnz) edge = __ldg(idx + e - 1) > __ldg(idx + e);
+        if (t == 0 && s != 0) bad = 1;
+        if (t == rows - 1 && (int64_t)e != nnz) bad = 1;
     }
-    const unsigned m_any = __ballot_sync(FULL, any), m_edge = __ballot_sync(FULL, edge);
+    const unsigned m_any = __ballot_sync(FULL, any), m_edge = __ballot_sync(FULL, edge), m_bad = __ballot_sync(FULL, bad);
     if (lane_id() == 0) {
-        if (m_any) atomicAdd(counts, __popc(m_any));
-        if (m_edge) atomicAdd(counts + 1, __popc(m_edge));
+        if (m_any) atomicAdd(flags + 1, __popc(m_any));
+        if (m_edge) atomicAdd(flags + 2, __popc(m_edge));
+        if (m_bad) atomicAdd(flags + 3, __popc(m_bad));
     }
 }
-__global__ void k_sorted_flag(const int32_t* __restrict__ counts, int32_t* __restrict__ flag) {
-    *flag = counts[0] == counts[1] ? 1 : 0;
+__global__ void k_sorted_flag(int32_t* __restrict__ flags) {
+    flags[0] = flags[1] == flags[2] ? 1 : 0;
 }
 
-cudaError_t launch_check_sorted(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_flag, int32_t* d_scratch2) {
-    cudaError_t e = cudaMemsetAsync(d_scratch2, 0, 2 * sizeof(int32_t), lc.stream);
+cudaError_t launch_check_csr(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_flags) {
+    cudaError_t e = cudaMemsetAsync(d_flags, 0, 4 * sizeof(int32_t), lc.stream);
     if (e != cudaSuccess) return e;
     const int64_t n = nnz > X.rows ? nnz : X.rows;
     if (n > 0) {
         const int threads = 256;
         const int64_t blocks = (n + threads - 1) / threads;
-        k_count_descents<<<(unsigned)blocks, threads, 0, lc.stream>>>(X.ptr, X.idx, X.rows, nnz, d_scratch2);
+        k_check_csr<<<(unsigned)blocks, threads, 0, lc.stream>>>(X.ptr, X.idx, X.rows, X.cols, nnz, d_flags);
         SB_LAUNCH_CHECK(lc);
     }
-    k_sorted_flag<<<1, 1, 0, lc.stream>>>(d_scratch2, d_flag);
+    k_sorted_flag<<<1, 1, 0, lc.stream>>>(d_flags);
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
 }
@@ -278,30 +289,88 @@ cudaError_t launch_transpose_fill(const LaunchCtx& lc, const Csr& X, const int32
     return cudaSuccess;
 }
 
-// Sort the entries of every (short) row by DESCENDING column, in place: one thread per row, insertion sort.
-// Used on H^T: the triple product's upper-triangle contraction then reads a row of H^T from the front and stops
-// at the first entry below the diagonal.  Rows longer than 64 entries are left alone and clear *flag.
+// Sort the entries of every row by column, in place, ascending or descending.  DESCENDING is used on H^T: the
+// triple product's upper-triangle contraction then reads a row of H^T from the front and stops at the first entry
+// below the diagonal.  ASCENDING is the device-side canonicalisation of an unsorted right operand (SURVEY.md 8(f).2;
+// the reference coerces on the host, sparse_matrix_mult/matrix_ops.py:307-310): the column-window kernels can then
+// binary-search instead of filtering every entry.  Duplicates stay (they are summed by the accumulators).
+//   k_sort_rows            one thread per row, insertion sort, rows of <= kSortShort entries (the common case: a row
+//                          of H^T holds the entries of one column of H); longer rows are appended to long_list
+//                          (long_list[0] = count, row ids from long_list[1])
+//   k_sort_long_rows       one block per listed row: bitonic network with every compare-exchange in the same
+//                          direction (first step of each merge mirrors the block), which sorts ANY length with
+//                          the out-of-range partners skipped; runs in global memory (rows of any length)
+constexpr int kSortShort = 32;
+
+template <bool DESC>
 __global__ void __launch_bounds__(256)
-k_sort_rows_desc(int rows, const int32_t* __restrict__ ptr, int32_t* __restrict__ idx, double* __restrict__ val,
-                 int32_t* __restrict__ flag) {
+k_sort_rows(int rows, const int32_t* __restrict__ ptr, int32_t* __restrict__ idx, double* __restrict__ val,
+            int32_t* __restrict__ long_list) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const int s = ptr[r], e = ptr[r + 1];
     if (e - s <= 1) return;
-    if (e - s > 64) { *flag = 0; return; }
+    if (e - s > kSortShort) { long_list[1 + atomicAdd(long_list, 1)] = r; return; }
     for (int a = s + 1; a < e; ++a) {
         const int k = idx[a];
         const double v = val[a];
         int b = a - 1;
-        while (b >= s && idx[b] < k) { idx[b + 1] = idx[b]; val[b + 1] = val[b]; --b; }
+        while (b >= s && (DESC ? idx[b] < k : idx[b] > k)) { idx[b + 1] = idx[b]; val[b + 1] = val[b]; --b; }
         idx[b + 1] = k;
         val[b + 1] = v;
     }
 }
-cudaError_t launch_sort_rows_desc(const LaunchCtx& lc, int rows, const int32_t* ptr, int32_t* idx, double* val,
-                                  int32_t* d_flag) {
+
+template <bool DESC>
+__global__ void __launch_bounds__(256)
+k_sort_long_rows(const int32_t* __restrict__ ptr, int32_t* idx, double* val, const int32_t* __restrict__ long_list) {
+    const int count = long_list[0];
+    for (int item = blockIdx.x; item < count; item += gridDim.x) {
+        const int r = long_list[1 + item];
+        const int s = ptr[r], n = ptr[r + 1] - s;
+        int32_t* ki = idx + s;
+        double* vi = val + s;
+        int np2 = 1;
+        while (np2 < n) np2 <<= 1;
+        const int half = np2 >> 1;
+        auto cmpx = [&](int i, int l) {              // DESC: keep the larger column at the lower position
+            const int a = ki[i], b = ki[l];
+            if (DESC ? a < b : a > b) {
+                ki[i] = b; ki[l] = a;
+                const double va = vi[i], vb = vi[l];
+                vi[i] = vb; vi[l] = va;
+            }
+        };
+        for (int k = 2; k <= np2; k <<= 1) {
+            const int hk = k >> 1;
+            for (int t = threadIdx.x; t < half; t += blockDim.x) {       // mirror step: i <-> block_end - offset
+                const int blk = t / hk, off = t % hk;
+                const int i = blk * k + off, l = blk * k + (k - 1 - off);
+                if (l < n) cmpx(i, l);
+            }
+            __syncthreads();
+            for (int j = k >> 2; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < half; t += blockDim.x) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i | j;
+                    if (l < n) cmpx(i, l);
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+cudaError_t launch_sort_rows(const LaunchCtx& lc, int rows, const int32_t* ptr, int32_t* idx, double* val,
+                             int32_t* d_long_list, bool descending) {
     if (rows <= 0) return cudaSuccess;
-    k_sort_rows_desc<<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, ptr, idx, val, d_flag);
+    cudaError_t e = cudaMemsetAsync(d_long_list, 0, sizeof(int32_t), lc.stream);
+    if (e != cudaSuccess) return e;
+    if (descending) k_sort_rows<true><<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, ptr, idx, val, d_long_list);
+    else k_sort_rows<false><<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, ptr, idx, val, d_long_list);
+    SB_LAUNCH_CHECK(lc);
+    if (descending) k_sort_long_rows<true><<<lc.sm_count * 4, 256, 0, lc.stream>>>(ptr, idx, val, d_long_list);
+    else k_sort_long_rows<false><<<lc.sm_count * 4, 256, 0, lc.stream>>>(ptr, idx, val, d_long_list);
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
 }

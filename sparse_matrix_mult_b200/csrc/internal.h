@@ -37,9 +37,9 @@ cudaError_t launch_row_products(const LaunchCtx& lc, const Csr& A, const Csr& B,
                                 bool upper_only, int64_t* d_prod, int32_t* d_nnz, int32_t* d_lists,
                                 int32_t* d_cursor, unsigned long long* d_total);
 
-// d_flag (int32, device) = 1 when every row of X has non-decreasing column indices, else 0.
-cudaError_t launch_check_sorted(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_flag,
-                                int32_t* d_scratch2 /* int32[2], zeroed by callee */);
+// d_flags (device int32[4]): [0] = 1 when every row of X has non-decreasing column indices, [3] = number of
+// invalid entries (column out of range, indptr not monotone / not ending at nnz); [1], [2] scratch.
+cudaError_t launch_check_csr(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_flags);
 
 // out[0] = 0, out[i+1] = out[i] + in[i]  (in int32[n], out OutT[n+1]); d_tmp holds >= 1025 int64.
 cudaError_t launch_scan_i64(const LaunchCtx& lc, const int32_t* in, int64_t* out, int n, int64_t* d_tmp);
@@ -54,9 +54,9 @@ cudaError_t launch_transpose_count(const LaunchCtx& lc, const Csr& X, int64_t nn
 cudaError_t launch_transpose_fill(const LaunchCtx& lc, const Csr& X, const int32_t* t_ptr, int32_t* d_cursor,
                                   int32_t* t_idx, double* t_val);
 
-// rows sorted by descending column, in place; *d_flag (preset to 1) is cleared when a row is too long to sort
-cudaError_t launch_sort_rows_desc(const LaunchCtx& lc, int rows, const int32_t* ptr, int32_t* idx, double* val,
-                                  int32_t* d_flag);
+// rows sorted by column (ascending or descending), in place, any row length; d_long_list: int32[rows + 1] scratch
+cudaError_t launch_sort_rows(const LaunchCtx& lc, int rows, const int32_t* ptr, int32_t* idx, double* val,
+                             int32_t* d_long_list, bool descending);
 cudaError_t launch_narrow_indptr(const LaunchCtx& lc, const int64_t* in, int32_t* out, int n);
 
 // cost model of the triple product rows (see spgemm_b200_row_costs)
@@ -86,10 +86,12 @@ cudaError_t launch_symmetrize(const LaunchCtx& lc, double* d_c, int n);
 cudaError_t dense_kernels_configure();
 
 // ---- triple.cu ----------------------------------------------------------------------------------
-// d_ht_desc: device flag, 1 when every row of Ht is sorted by descending column (null = unknown -> filter)
-cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, const int32_t* d_ht_desc,
+// ht_desc: every row of Ht is sorted by descending column (false = unknown -> every entry is filtered);
+// ht_nnz picks the lanes per row of H^T; mode 0 = shared-memory window kernel, 2 = round-1 L2-reduction kernel
+cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool ht_desc,
                           bool upper_only, int row_begin, int nrows, double* d_c,
-                          unsigned long long* d_counters /* [3], zeroed: P1, P2, row ticket */, int mode);
+                          unsigned long long* d_counters /* [3], zeroed: P1, P2, row ticket */, int64_t ht_nnz,
+                          int mode);
 cudaError_t triple_kernels_configure();
 
 }  // namespace sb

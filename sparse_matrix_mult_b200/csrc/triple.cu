@@ -1,12 +1,20 @@
 // triple.cu -- fused triple product C = H Q H^T into a dense row-major float64 matrix.
 //
 // Replaces triple_product (/root/reference/src/sparse_sparse_dense.cpp:141-249).  The reference expands
-// t = H[i,:] Q into a dense scratch row and then takes a sparse dot of t with EVERY row r >= i of H
-// (n(n+1)/2 * nnz/row gathers).  Here a thread block owns (row i, column tile): it streams the products
-// w = h_ij * q_jc of the expansion (never stored) and contracts each against row c of H^T, scatter-adding
-// w * h_rc into the tile of C[i, :] held in shared memory; the tile then leaves with 128-bit streaming
-// stores.  Work is P1 + P2 instead of n^2 * nnz/row, H Q is never materialised, and C is
-// written once.
+// t = H[i,:] Q into a dense scratch row (:187-198) and then takes a sparse dot of t with EVERY row k >= i of H
+// (:201-216, n(n+1)/2 * nnz/row gathers).  Here a thread block owns row i of C: it streams the products
+// w = h_ij * q_jc of the expansion (never stored) and contracts each against row c of H^T,
+// C[i,k] += w * h_kc for k >= i.  Work is P1 + P2 instead of n^2/2 * nnz/row, H Q is never
+// materialised, and every byte of C is written once.
+//
+// k_triple_window (default): the row's accumulator lives in SHARED memory -- a window of up to ~26,800 doubles
+// starting at the diagonal; columns beyond the window (only the first rows of very wide outputs have any) are
+// accumulated with float64 reductions that resolve in L2.  Shared-memory accumulation runs at 2-3x the chip-wide
+// L2 reduction rate (scripts/micro/atomic_bw.cu: 540 vs 197 G adds/s), needs no L2 residency of the C rows in
+// flight, and the finished window leaves with coalesced 128-bit streaming stores.
+// k_triple_rows_red (round 1, kept selectable for A/B runs: SPGEMM_B200_TRIPLE_MODE=2): every add is an L2 reduction.
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace sb {
@@ -17,9 +25,6 @@ namespace sb {
         cudaError_t e_ = cudaGetLastError(); \
         if (e_ != cudaSuccess) return e_;    \
     } while (0)
-
-constexpr int kTripleThreads = 512;
-constexpr int kTripleTileMax = 12288;
 
 __device__ __forceinline__ void triple_stream_out(double* __restrict__ dst, const double* src, int count) {
     if (count <= 0) return;
@@ -52,72 +57,197 @@ __device__ __forceinline__ void triple_flush_counters(unsigned long long p1, uns
     if (threadIdx.x < 2 && s_cnt[threadIdx.x]) atomicAdd(counters + threadIdx.x, s_cnt[threadIdx.x]);
 }
 
-template <bool UPPER>
-__global__ void __launch_bounds__(kTripleThreads)
-k_triple_tiles(Csr H, Csr Q, Csr Ht, const int32_t* __restrict__ ht_desc, int row_begin, int nrows, int tile_w,
-               int ntiles, double* __restrict__ C, unsigned long long* __restrict__ counters) {
-    extern __shared__ double acc[];
-    __shared__ unsigned long long s_cnt[2];
-    __shared__ SegScratch<kTripleThreads> s_seg;
-    const int n = H.rows;
-    const bool desc = ht_desc != nullptr && *ht_desc != 0;
-    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    unsigned long long p1 = 0, p2 = 0;
-    for (int64_t item = blockIdx.x; item < (int64_t)nrows * ntiles; item += gridDim.x) {
-        const int r = (int)(item / ntiles), t = (int)(item % ntiles);
-        const int i = row_begin + r;
-        const int t0 = t * tile_w, t1 = min(n, t0 + tile_w);
-        const int lo = UPPER ? max(t0, i) : t0;
-        const int first_t = UPPER ? i / tile_w : 0;
-        const int h_begin = __ldg(H.ptr + i), h_end = __ldg(H.ptr + i + 1);
-        double* out = C + (size_t)r * n + t0;
-        if (h_begin == h_end || lo >= t1) {
-            triple_stream_out(out, nullptr, t1 - t0);
-            continue;
-        }
-        for (int x = threadIdx.x; x < t1 - t0; x += blockDim.x) acc[x] = 0.0;
-        __syncthreads();
-        expand_row_block<true>(H, Q, h_begin, h_end, 0, 0, false, false, s_seg, [&](int c, double w) {
-            if (t == first_t) ++p1;                 // count the expansion once per row, not per tile
-            const int s = __ldg(Ht.ptr + c), e = __ldg(Ht.ptr + c + 1);
-            for (int q = s; q < e; ++q) {
-                const int k = __ldg(Ht.idx + q);
-                if (k < lo) { if (desc) break; else continue; }     // descending rows: nothing useful follows
-                if (k < t1) {
-                    atomicAdd(acc + (k - t0), w * __ldg(Ht.val + q));
-                    ++p2;
-                }
-            }
-        });
-        __syncthreads();
-        triple_stream_out(out, acc, t1 - t0);
-        __syncthreads();
-    }
-    triple_flush_counters(p1, p2, s_cnt, counters);
+// ---------------------------------------------------------------------------------------------------
+// Shared-memory window kernel.
+//
+// Per row i (rows handed out in order through an atomic ticket: upper-triangle rows get cheaper towards the
+// bottom, so in-order dynamic scheduling is longest-first):
+//   1. up to blockDim entries (j, h_ij) of H[i,:] are loaded one per thread together with the extent of row j of Q;
+//      a block-wide prefix sum numbers the products of the expansion 0..total-1;
+//   2. the product range is cut into equal contiguous shares, one per warp: lane l of a warp takes product
+//      f0 + l, finds its row of Q in the prefix table (same row as its neighbour almost always: one shared-memory
+//      probe), loads (c, q_jc) -- coalesced, a row of Q is contiguous -- and the extent of row c of H^T;
+//   3. contraction: the warp's 32 products are handed to sub-warp groups of G lanes (G ~ the mean row length of
+//      H^T), each lane walks its product's row of H^T with stride G.  Rows of H^T are sorted by DESCENDING k
+//      (transpose_impl), so the walk stops at the first k below the diagonal.  The first loads of four rounds
+//      are issued before any of them is used (memory-level parallelism instead of a serial per-thread walk).
+//   4. adds go to the shared window [w0, w1) (CAS loop on float64) or, beyond it, to C itself (L2 reduction);
+//   5. the window is streamed out and cleared in one pass.
+// Dynamic shared memory: acc[win_cap] | hv[blockDim] (h_ij) | qs[blockDim] (first entry of row j of Q) |
+// pre[blockDim + 1] (exclusive prefix of the Q row lengths).
+struct TripleScratch {
+    unsigned red[33];
+    unsigned long long cnt[2];
+    int row;
+};
+__host__ __device__ inline size_t triple_window_smem(int win_cap, int threads) {
+    return (size_t)win_cap * 8 + (size_t)threads * 16 + 16;
 }
 
-// Variant without a shared-memory tile: the block owns a whole row of C, streams zeros over it while the
-// gathers of H[i,:] are in flight, then adds every contribution with a float64 reduction that resolves in L2
-// (native RED.ADD.F64 -- the shared-memory path needs a compare-and-swap loop per add).
-// The rows being accumulated must stay L2 resident (a reduction that misses L2 is a DRAM read-modify-write, ~8x
-// slower): the grid is persistent and sized so that rows-in-flight x 8n bytes fits a share of the 126 MB L2;
-// wide outputs therefore run one 1024-thread block per SM instead of eight 256-thread blocks.
+template <bool UPPER, int G>
+__global__ void __launch_bounds__(1024, 1)
+k_triple_window(Csr H, Csr Q, Csr Ht, int ht_desc, int row_begin, int nrows, int win_cap,
+                double* __restrict__ C, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ TripleScratch S;
+    const int n = H.rows;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* acc = reinterpret_cast<double*>(s_raw);
+    double* s_hv = acc + win_cap;                                   // win_cap is even: 16-byte aligned
+    int* s_qs = reinterpret_cast<int*>(s_hv + nt);
+    unsigned* s_pre = reinterpret_cast<unsigned*>(s_qs + nt);
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+    constexpr int NG = 32 / G;                 // groups per warp; a warp's 32 products take G rounds
+    constexpr int BATCH = G < 4 ? G : 4;       // rounds whose first loads are in flight together
+    const int grp = lane / G, sub = lane % G;
+    const bool desc = ht_desc != 0;
+    if (tid < 2) S.cnt[tid] = 0;
+    for (int t = tid; t < win_cap; t += nt) acc[t] = 0.0;
+    __syncthreads();
+    unsigned long long p1 = 0, p2 = 0;
+    while (true) {
+        if (tid == 0) S.row = (int)atomicAdd(counters + 2, 1ULL);
+        __syncthreads();
+        const int r = S.row;
+        __syncthreads();
+        if (r >= nrows) break;
+        const int i = row_begin + r;
+        const int lo = UPPER ? i : 0;
+        const int w0 = lo, w1 = min(n, lo + win_cap);
+        double* row = C + (size_t)r * n;
+        const int h_begin = __ldg(H.ptr + i), h_end = __ldg(H.ptr + i + 1);
+        // zeros left of the diagonal (never touched again: evict-first) and right of the window (about to take
+        // reductions: default policy so the lines stay in L2)
+        triple_stream_out(row, nullptr, w0);
+        for (int t = w1 + tid; t < n; t += nt) row[t] = 0.0;
+        for (int base = h_begin; base < h_end; base += nt) {
+            const int cnt = min(nt, h_end - base);
+            int qs = 0;
+            unsigned len = 0;
+            if (tid < cnt) {
+                const int j = __ldg(H.idx + base + tid);
+                qs = __ldg(Q.ptr + j);
+                len = (unsigned)(__ldg(Q.ptr + j + 1) - qs);
+                s_hv[tid] = __ldg(H.val + base + tid);
+                s_qs[tid] = qs;
+            }
+            unsigned total;
+            const unsigned ex = block_excl_scan<unsigned>(len, S.red, &total);
+            if (tid < cnt) s_pre[tid] = ex;
+            if (tid == 0) s_pre[cnt] = total;
+            __syncthreads();                               // tables complete; tail zeros ordered before reductions
+            if (tid == 0) p1 += total;
+            const unsigned wb = (unsigned)((unsigned long long)total * warp / nwarp);
+            const unsigned we = (unsigned)((unsigned long long)total * (warp + 1) / nwarp);
+            int r_base = 0;
+            if (wb < we) {                                 // row of the warp's first product (warp-uniform search)
+                int a = 0, b = cnt;
+                while (b - a > 1) {
+                    const int mid = (a + b) >> 1;
+                    if (s_pre[mid] <= wb) a = mid; else b = mid;
+                }
+                r_base = a;
+            }
+            for (unsigned f0 = wb; f0 < we; f0 += 32) {
+                const unsigned f = f0 + lane;
+                const bool valid = f < we;
+                int rr = r_base;
+                int hs = 0, he = 0;
+                double w = 0.0;
+                if (valid) {
+                    if (s_pre[rr + 1] <= f) {              // beyond the base row: largest rr with pre[rr] <= f
+                        int a = rr + 1, b = cnt;
+                        while (b - a > 1) {
+                            const int mid = (a + b) >> 1;
+                            if (s_pre[mid] <= f) a = mid; else b = mid;
+                        }
+                        rr = a;
+                    }
+                    const int q = s_qs[rr] + (int)(f - s_pre[rr]);
+                    const int c = __ldg(Q.idx + q);
+                    w = s_hv[rr] * __ldg(Q.val + q);
+                    hs = __ldg(Ht.ptr + c);
+                    he = __ldg(Ht.ptr + c + 1);
+                }
+                const unsigned last = min(31u, we - f0 - 1u);
+                r_base = __shfl_sync(FULL, rr, (int)last);
+                // contraction of the warp's 32 products, G lanes per product
+#pragma unroll 1
+                for (int rd = 0; rd < G; rd += BATCH) {
+                    int q[BATCH], pe[BATCH], k[BATCH];
+                    double pw[BATCH], v[BATCH];
+#pragma unroll
+                    for (int b = 0; b < BATCH; ++b) {
+                        const int p = (rd + b) * NG + grp;
+                        q[b] = __shfl_sync(FULL, hs, p) + sub;
+                        pe[b] = __shfl_sync(FULL, he, p);
+                        pw[b] = __shfl_sync(FULL, w, p);
+                        k[b] = q[b] < pe[b] ? __ldg(Ht.idx + q[b]) : -1;
+                    }
+#pragma unroll
+                    for (int b = 0; b < BATCH; ++b) v[b] = k[b] >= lo ? __ldg(Ht.val + q[b]) : 0.0;
+#pragma unroll
+                    for (int b = 0; b < BATCH; ++b) {
+                        if (k[b] >= lo) {
+                            const double x = pw[b] * v[b];
+                            if (k[b] < w1) atomicAdd(acc + (k[b] - w0), x); else atomicAdd(row + k[b], x);
+                            ++p2;
+                        }
+                        // rest of a row of H^T longer than G (descending rows: a cut lane has nothing further)
+                        if (k[b] >= lo || (!desc && k[b] >= 0)) {
+                            for (int qq = q[b] + G; qq < pe[b]; qq += G) {
+                                const int kk = __ldg(Ht.idx + qq);
+                                if (kk < lo) { if (desc) break; else continue; }
+                                const double x = pw[b] * __ldg(Ht.val + qq);
+                                if (kk < w1) atomicAdd(acc + (kk - w0), x); else atomicAdd(row + kk, x);
+                                ++p2;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();                               // tables are rewritten by the next slice / row
+        }
+        // window out (coalesced 128-bit streaming stores) and cleared for the next row
+        {
+            const int count = w1 - w0;
+            double* dst = row + w0;
+            const int head = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1);
+            if (head && tid == 0 && count > 0) { st_stream_f64(dst, acc[0]); acc[0] = 0.0; }
+            const int pairs = (count - head) >> 1;
+            double* d2 = dst + head;
+            double* s2 = acc + head;
+            for (int t = tid; t < pairs; t += nt) {
+                st_stream_f64x2(d2 + 2 * t, s2[2 * t], s2[2 * t + 1]);
+                s2[2 * t] = 0.0;
+                s2[2 * t + 1] = 0.0;
+            }
+            const int tail = head + 2 * pairs;
+            if (tail < count && tid == nt - 1) { st_stream_f64(dst + tail, acc[tail]); acc[tail] = 0.0; }
+        }
+        // (the ticket barrier at the top of the loop orders the clearing before the next row's adds)
+    }
+    triple_flush_counters(p1, p2, S.cnt, counters);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Round-1 kernel: the block owns a whole row of C in global memory, streams zeros over it and adds every
+// contribution with a float64 reduction that resolves in L2.  The rows being accumulated must stay L2 resident
+// (a reduction that misses L2 is a DRAM read-modify-write), so the grid is persistent and sized so that
+// rows-in-flight x 8n bytes fits a share of the 126 MB L2.
 template <bool UPPER, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_triple_rows_red(Csr H, Csr Q, Csr Ht, const int32_t* __restrict__ ht_desc, int row_begin, int nrows,
+k_triple_rows_red(Csr H, Csr Q, Csr Ht, int ht_desc, int row_begin, int nrows,
                   double* __restrict__ C, unsigned long long* __restrict__ counters) {
     __shared__ unsigned long long s_cnt[2];
     __shared__ SegScratch<THREADS> s_seg;
     const int n = H.rows;
-    const bool desc = ht_desc != nullptr && *ht_desc != 0;
+    const bool desc = ht_desc != 0;
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     unsigned long long p1 = 0, p2 = 0;
     __shared__ int s_row;
     while (true) {
-        // rows are handed out in order through counters[2] (upper-triangle rows get cheaper towards the bottom,
-        // so in-order dynamic scheduling is longest-first)
         if (threadIdx.x == 0) s_row = (int)atomicAdd(counters + 2, 1ULL);
         __syncthreads();
         const int r = s_row;
@@ -142,26 +272,55 @@ k_triple_rows_red(Csr H, Csr Q, Csr Ht, const int32_t* __restrict__ ht_desc, int
     triple_flush_counters(p1, p2, s_cnt, counters);
 }
 
-static size_t g_triple_smem_optin = 0;
+// ---------------------------------------------------------------------------------------------------
+static size_t g_triple_smem_optin = 0, g_triple_smem_sm = 0;
+
+template <bool UPPER, int G>
+static cudaError_t configure_window() {
+    return cudaFuncSetAttribute(k_triple_window<UPPER, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(g_triple_smem_optin - sizeof(TripleScratch) - 64));
+}
 
 cudaError_t triple_kernels_configure() {
-    int dev = 0, optin = 0;
+    int dev = 0, optin = 0, per_sm = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
-    g_triple_smem_optin = (size_t)optin;
-    e = cudaFuncSetAttribute(k_triple_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
+    e = cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_triple_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
+    g_triple_smem_optin = (size_t)optin;
+    g_triple_smem_sm = (size_t)per_sm;
+    if ((e = configure_window<true, 4>()) != cudaSuccess) return e;
+    if ((e = configure_window<true, 8>()) != cudaSuccess) return e;
+    if ((e = configure_window<true, 32>()) != cudaSuccess) return e;
+    if ((e = configure_window<false, 4>()) != cudaSuccess) return e;
+    if ((e = configure_window<false, 8>()) != cudaSuccess) return e;
+    return configure_window<false, 32>();
 }
 
-cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, const int32_t* d_ht_desc,
-                          bool upper_only,
-                          int row_begin, int nrows, double* d_c, unsigned long long* d_counters, int mode) {
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+template <bool UPPER>
+static void launch_window(int group, int grid, int threads, size_t smem, cudaStream_t st, const Csr& H, const Csr& Q,
+                          const Csr& Ht, int ht_desc, int row_begin, int nrows, int win_cap, double* d_c,
+                          unsigned long long* d_counters) {
+    if (group <= 4)
+        k_triple_window<UPPER, 4><<<grid, threads, smem, st>>>(H, Q, Ht, ht_desc, row_begin, nrows, win_cap, d_c, d_counters);
+    else if (group <= 8)
+        k_triple_window<UPPER, 8><<<grid, threads, smem, st>>>(H, Q, Ht, ht_desc, row_begin, nrows, win_cap, d_c, d_counters);
+    else
+        k_triple_window<UPPER, 32><<<grid, threads, smem, st>>>(H, Q, Ht, ht_desc, row_begin, nrows, win_cap, d_c, d_counters);
+}
+
+cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool ht_desc,
+                          bool upper_only, int row_begin, int nrows, double* d_c, unsigned long long* d_counters,
+                          int64_t ht_nnz, int mode) {
     const int n = H.rows;
     if (nrows <= 0 || n <= 0) return cudaSuccess;
-    if (mode == 0) mode = 2;
     if (mode == 2) {
         const double l2_budget = 64.0e6;                                  // bytes of C rows in flight
         const double row_bytes = 8.0 * n * (upper_only ? 0.6 : 1.0);      // upper rows touch [i, n) only
@@ -171,37 +330,47 @@ cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const
         const int per_sm = big ? 1 : (rows_in_flight / lc.sm_count > 8 ? 8 : rows_in_flight / lc.sm_count);
         int grid = lc.sm_count * per_sm;
         if (grid > nrows) grid = nrows;
+        const int d = ht_desc ? 1 : 0;
         if (big) {
             if (upper_only)
-                k_triple_rows_red<true, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, d_ht_desc, row_begin, nrows, d_c, d_counters);
+                k_triple_rows_red<true, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
             else
-                k_triple_rows_red<false, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, d_ht_desc, row_begin, nrows, d_c, d_counters);
+                k_triple_rows_red<false, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
         } else {
             if (upper_only)
-                k_triple_rows_red<true, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, d_ht_desc, row_begin, nrows, d_c, d_counters);
+                k_triple_rows_red<true, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
             else
-                k_triple_rows_red<false, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, d_ht_desc, row_begin, nrows, d_c, d_counters);
+                k_triple_rows_red<false, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
         }
         SB_LAUNCH_CHECK(lc);
         return cudaSuccess;
     }
-    int ntiles = (n + kTripleTileMax - 1) / kTripleTileMax;
-    int tile_w = (n + ntiles - 1) / ntiles;
-    tile_w = (tile_w + 1) & ~1;
-    ntiles = (n + tile_w - 1) / tile_w;
-    const size_t smem = (size_t)tile_w * sizeof(double);
-    const int64_t items = (int64_t)nrows * ntiles;
-    int per_sm = (int)(g_triple_smem_optin / (smem + 10240));
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm < 1) per_sm = 1;
-    int64_t grid = (int64_t)lc.sm_count * per_sm * 8;
-    if (grid > items) grid = items;
-    if (upper_only)
-        k_triple_tiles<true><<<(unsigned)grid, kTripleThreads, smem, lc.stream>>>(H, Q, Ht, d_ht_desc, row_begin, nrows, tile_w,
-                                                                                   ntiles, d_c, d_counters);
-    else
-        k_triple_tiles<false><<<(unsigned)grid, kTripleThreads, smem, lc.stream>>>(H, Q, Ht, d_ht_desc, row_begin, nrows, tile_w,
-                                                                                    ntiles, d_c, d_counters);
+    // ---- shared-memory window kernel ----
+    // window: the widest row segment this launch accumulates (row `row_begin` in upper mode), capped by what one
+    // block may hold; 1, 2 or 4 blocks per SM of 1024 / 512 / 256 threads (32 warps per SM at <= 64 registers)
+    const size_t fixed = sizeof(TripleScratch) + 1024;                    // static scratch + per-block reserve
+    const int cap_max = (int)(((g_triple_smem_optin - sizeof(TripleScratch) - 64 - triple_window_smem(0, 1024)) / 8) & ~(size_t)1);
+    int need = upper_only ? n - row_begin : n;
+    need = (need + 1) & ~1;
+    if (need < 2) need = 2;
+    int win = need < cap_max ? need : cap_max;
+    if (const int o = env_int("SPGEMM_B200_TRIPLE_WIN", 0))              // experiments: force the window / residency
+        win = (o < cap_max ? o : cap_max) & ~1;
+    int per_sm = 1;
+    for (int cand : {4, 2}) {
+        if (g_triple_smem_sm / (triple_window_smem(win, 1024 / cand) + fixed) >= (size_t)cand) { per_sm = cand; break; }
+    }
+    const int threads = 1024 / per_sm;
+    int grid = lc.sm_count * per_sm;
+    if (grid > nrows) grid = nrows;
+    // lanes per row of H^T ~ its mean length (upper mode keeps about half of each row on average)
+    const double mean_len = Ht.rows > 0 ? (double)ht_nnz / (double)Ht.rows : 1.0;
+    int group = mean_len <= 10.0 ? 4 : mean_len <= 24.0 ? 8 : 32;
+    group = env_int("SPGEMM_B200_TRIPLE_GROUP", group);
+    const size_t smem = triple_window_smem(win, threads);
+    const int d = ht_desc ? 1 : 0;
+    if (upper_only) launch_window<true>(group, grid, threads, smem, lc.stream, H, Q, Ht, d, row_begin, nrows, win, d_c, d_counters);
+    else launch_window<false>(group, grid, threads, smem, lc.stream, H, Q, Ht, d, row_begin, nrows, win, d_c, d_counters);
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
 }

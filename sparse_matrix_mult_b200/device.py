@@ -83,9 +83,20 @@ class DeviceMatrix:
         return cls(h, shape, nnz, keep)
 
     def transpose(self):
+        """X^T on the device, rows sorted by descending column (what the triple product wants for H^T)."""
         h = _vp()
         _check(matrix_ops.get_lib().spgemm_b200_mat_transpose(self._h, ctypes.byref(h)), "spgemm_b200_mat_transpose")
         return DeviceMatrix(h, self.shape[::-1], self.nnz)
+
+    def is_sorted(self):
+        r = matrix_ops.get_lib().spgemm_b200_mat_is_sorted(self._h)
+        if r < 0:
+            _check(1, "spgemm_b200_mat_is_sorted")
+        return bool(r)
+
+    def sort_rows(self):
+        """Device-side canonicalisation: rows sorted by ascending column (duplicates stay)."""
+        _check(matrix_ops.get_lib().spgemm_b200_mat_sort(self._h), "spgemm_b200_mat_sort")
 
     def free(self):
         if self._h:
@@ -200,7 +211,7 @@ class SharedDense:
 
 def _rows(a, row_begin, row_end):
     if row_end is None:
-        return 0, a.shape[0]
+        return int(row_begin), a.shape[0]
     return int(row_begin), int(row_end)
 
 

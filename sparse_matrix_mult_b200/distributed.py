@@ -47,8 +47,10 @@ def host_row_costs(a, b, kind, upper_only):
         return p1
     ht_len = np.bincount(a.indices, minlength=a.shape[1]).astype(np.int64)      # nnz of rows of H^T
     # sum over (i,j) in H of sum_{c in Q_j} nnz(H^T_c): cost of row j of Q first, then gather by H's columns
-    qcost = np.add.reduceat(ht_len[b.indices], b.indptr[:-1]) if b.nnz else np.zeros(b.shape[0])
-    qcost = np.where(np.diff(b.indptr) > 0, qcost, 0).astype(np.float64)
+    # (cumulative sum differenced at the row pointers: np.add.reduceat rejects the index nnz that trailing empty
+    #  rows of Q put into indptr[:-1])
+    cum = np.concatenate([[0], np.cumsum(ht_len[b.indices])])
+    qcost = (cum[b.indptr[1:]] - cum[b.indptr[:-1]]).astype(np.float64)
     p2 = np.bincount(rows, weights=qcost[a.indices], minlength=a.shape[0])
     if upper_only:
         n = a.shape[0]

@@ -12,7 +12,13 @@ Deliberate deviations from the reference (all documented in DESIGN.md):
   * CUDA / allocation failures raise RuntimeError instead of being swallowed into a zero matrix
     (matrix_ops.py:377-387); an invalid `output_format` still prints and returns zeros as the reference does;
   * sparse results have sorted column indices (the reference's are in first-touch order);
-  * `mirror=True` (new keyword, default off) fills the lower triangle of symmetric dense results on the GPU.
+  * `mirror=True` (new keyword, default off) fills the lower triangle of symmetric dense results on the GPU;
+  * `n_gpus=N` (new keyword; default: the SPGEMM_NUM_GPUS environment variable, else 1) shards the rows of the
+    product over N GPUs of the box inside the call -- one host thread per GPU in the library, the way the
+    reference sizes its OpenMP team inside the call (src/sparse_sparse_sparse.cpp:188-197).
+
+Thread safety: the library serialises concurrent calls per device (include/spgemm_b200.h, "Thread safety"), so
+sparse_matrix_multiply may be called from several Python threads.
 """
 import ctypes
 import os
@@ -122,6 +128,19 @@ class MatrixOpsLibrary:
         L.spgemm_b200_ipc_close.argtypes = [_vp]
         L.spgemm_b200_set_stream.argtypes = [_vp]
         L.spgemm_b200_timer_stop.argtypes = [ctypes.POINTER(ctypes.c_double)]
+        L.spgemm_b200_trim.argtypes = [ctypes.c_size_t]
+        L.spgemm_b200_mat_sort.argtypes = [_vp]
+        L.spgemm_b200_mat_is_sorted.argtypes = [_vp]
+        L.spgemm_b200_multi_dense.argtypes = [ctypes.c_int] * 4 + csr + csr + [ctypes.c_int, _f64p]
+        L.spgemm_b200_multi_triple.argtypes = [ctypes.c_int] * 3 + csr + csr + [_f64p]
+        L.spgemm_b200_multi_csr.argtypes = [ctypes.c_int] * 4 + csr + csr + [ctypes.c_int, ctypes.POINTER(_vp)]
+        L.spgemm_b200_multi_result_nnz.argtypes = [_vp]
+        L.spgemm_b200_multi_result_nnz.restype = ctypes.c_int64
+        L.spgemm_b200_multi_result_copy.argtypes = [_vp, _vp, ctypes.c_int, _i32p, _f64p]
+        L.spgemm_b200_multi_result_free.argtypes = [_vp]
+        L.spgemm_b200_multi_result_free.restype = None
+        L.spgemm_b200_multi_last_bounds.argtypes = [_i32p, ctypes.c_int]
+        L.spgemm_b200_multi_last_stats.argtypes = [ctypes.c_int, ctypes.POINTER(Stats)]
 
     def get_lib(self):
         if self._lib is None:
@@ -199,9 +218,10 @@ def _ptrs(arrs):
     return p.ctypes.data_as(_i32p), i.ctypes.data_as(_i32p), v.ctypes.data_as(_f64p)
 
 
-def result_to_csr(lib, handle, shape):
-    """Device result -> scipy CSR (reference: sparsemat_to_csr, matrix_ops.py:205-228)."""
-    nnz = lib.spgemm_b200_result_nnz(handle)
+def result_to_csr(lib, handle, shape, multi=False):
+    """Device result -> scipy CSR (reference: sparsemat_to_csr, matrix_ops.py:205-228).  multi: the handle is a
+    spgemm_b200_multi_result (row blocks on several GPUs, copied out in parallel)."""
+    nnz = (lib.spgemm_b200_multi_result_nnz if multi else lib.spgemm_b200_result_nnz)(handle)
     if nnz == 0:
         return csr_matrix(shape)
     if nnz >= 2 ** 31:
@@ -210,15 +230,40 @@ def result_to_csr(lib, handle, shape):
     indptr = _result_array((shape[0] + 1,), np.int32)
     indices = _result_array((nnz,), np.int32)
     data = _result_array((nnz,), np.float64)
-    _check(lib.spgemm_b200_result_copy(handle, indptr.ctypes.data_as(_vp), 0, indices.ctypes.data_as(_i32p),
-                                       data.ctypes.data_as(_f64p)), "spgemm_b200_result_copy")
+    copy = lib.spgemm_b200_multi_result_copy if multi else lib.spgemm_b200_result_copy
+    _check(copy(handle, indptr.ctypes.data_as(_vp), 0, indices.ctypes.data_as(_i32p), data.ctypes.data_as(_f64p)),
+           "spgemm_b200_result_copy")
     out = csr_matrix((data, indices, indptr), shape=shape, copy=False)
     out.has_sorted_indices = True
     return out
 
 
+def multi_last_bounds():
+    """Row bounds (len n_gpus + 1) the last n_gpus > 1 call sharded by."""
+    buf = (ctypes.c_int32 * 64)()
+    n = matrix_ops.get_lib().spgemm_b200_multi_last_bounds(buf, 64)
+    return [int(buf[i]) for i in range(min(n, 64))]
+
+
+def multi_last_stats():
+    """Per-GPU stats dicts of the last n_gpus > 1 call."""
+    lib, out = matrix_ops.get_lib(), []
+    for part in range(max(0, len(multi_last_bounds()) - 1)):
+        s = Stats()
+        _check(lib.spgemm_b200_multi_last_stats(part, ctypes.byref(s)), "spgemm_b200_multi_last_stats")
+        out.append(s.as_dict())
+    return out
+
+
+def _default_gpus():
+    try:
+        return max(1, int(os.environ.get("SPGEMM_NUM_GPUS", "1")))
+    except ValueError:
+        return 1
+
+
 def sparse_matrix_multiply(matrix_a, matrix_b, output_format='sparse', symmetric=False, imem_size=None,
-                           use_triple_product=False, compute_full_matrix=None, mirror=False):
+                           use_triple_product=False, compute_full_matrix=None, mirror=False, n_gpus=None):
     """Multiply two sparse matrices on a B200.  Signature and semantics of
     /root/reference/sparse_matrix_mult/matrix_ops.py:271-387.
 
@@ -231,6 +276,9 @@ def sparse_matrix_multiply(matrix_a, matrix_b, output_format='sparse', symmetric
                          i.e. T + T.T - diag(T) of the full product T.
     mirror             : extension.  With symmetric=True, output_format='dense' (or the triple product with
                          compute_full_matrix in (None, 0)) also fill the lower triangle with the mirror image.
+    n_gpus             : extension.  Shard the rows of the product over this many GPUs of the box inside the call
+                         (default: $SPGEMM_NUM_GPUS, else 1).  The modes that need the whole matrix on one device
+                         (mirror=True, compute_full_matrix=1) always run on one GPU.
     """
     # -- argument handling: matrix_ops.py:288-305 ----------------------------------------------------
     if imem_size is None:
@@ -272,6 +320,11 @@ def sparse_matrix_multiply(matrix_a, matrix_b, output_format='sparse', symmetric
 
     lib = matrix_ops.get_lib()
     a_arr, b_arr = csr_to_arrays(matrix_a), csr_to_arrays(matrix_b)
+    n_gpus = _default_gpus() if n_gpus is None else int(n_gpus)
+    if n_gpus < 1:
+        raise ValueError("n_gpus must be a positive integer")
+    if n_gpus > 1 and not (mirror or (use_triple_product and compute_full_matrix)):
+        return _multiply_multi(lib, n_gpus, a_arr, b_arr, (m, k, n), output_format, symmetric, use_triple_product)
     if use_triple_product:
         # like the reference (matrix_ops.py:312-313 is the only check) Q is assumed square with H.cols rows;
         # unlike it, a violation is reported instead of reading out of bounds
@@ -297,4 +350,31 @@ def sparse_matrix_multiply(matrix_a, matrix_b, output_format='sparse', symmetric
 
     if isinstance(result, csr_matrix) and result.nnz == 0:
         print("Multiplication resulted in a zero matrix.")
+    return result
+
+
+def _multiply_multi(lib, n_gpus, a_arr, b_arr, dims, output_format, symmetric, use_triple_product):
+    """The n_gpus > 1 legs of sparse_matrix_multiply: same dispatch precedence, multi-GPU entry points."""
+    m, k, n = dims
+    if use_triple_product:
+        if k != n:
+            raise ValueError("Triple product needs a square second matrix (H @ Q @ H.T).")
+        result = _result_array((m, m), np.float64)
+        _check(lib.spgemm_b200_multi_triple(n_gpus, m, k, *_ptrs(a_arr), *_ptrs(b_arr), result.ctypes.data_as(_f64p)),
+               "spgemm_b200_multi_triple")
+        return result
+    if output_format == 'sparse':
+        handle = _vp()
+        _check(lib.spgemm_b200_multi_csr(n_gpus, m, k, n, *_ptrs(a_arr), *_ptrs(b_arr), 1 if symmetric else 0,
+                                         ctypes.byref(handle)), "spgemm_b200_multi_csr")
+        try:
+            result = result_to_csr(lib, handle, (m, n), multi=True)
+        finally:
+            lib.spgemm_b200_multi_result_free(handle)
+        if result.nnz == 0:
+            print("Multiplication resulted in a zero matrix.")
+        return result
+    result = _result_array((m, n), np.float64)
+    _check(lib.spgemm_b200_multi_dense(n_gpus, m, k, n, *_ptrs(a_arr), *_ptrs(b_arr), 1 if symmetric else 0,
+                                       result.ctypes.data_as(_f64p)), "spgemm_b200_multi_dense")
     return result
