@@ -1,22 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- SpGEMM throughput of the B200 path on the BASELINE.json configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5] [--impl ours|reference]
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one synthetic input:
   value    : whole-job GFLOP/s (2 * intermediate products / time) with the operands already in HBM,
              timed per step with CUDA events on the library stream (max over ranks for N > 1)
-  e2e      : the same metric through the public API sparse_matrix_multiply() with HOST operands in
+  e2e      : the same metric through the public API sparse_matrix_multiply(..., n_gpus=N) with HOST operands in
              pinned memory and a HOST result: H2D + kernels + D2H all inside the timed region
   roofline : the dominant kernel of the workload against the measured HBM copy bandwidth
   cpu_baseline : the reference's own C routine (oracle/_ref) on this box's host cores, bounded sample
+  per_config   : (N = 1, default workload only) value / roofline / e2e of the other BASELINE configs
+  parity       : (N > 1) checksums of every rank's row block against the same rows of a one-GPU run
 
-Default workload = BASELINE.json configs[1] (A 20,000 x 50,000, density 5e-4, A*A^T -> symmetric dense):
-the largest config the reference itself can also run on the host.  Other workloads: cfg1 cfg3 cfg4r cfg4 cfg5
-(and the reduced cfg1s cfg2s cfg3s cfg5s cfg4r<scale>).  --impl reference times the reference's CPU
-implementation of the same workload (rank 0 only).
+Default workload = BASELINE.json configs[4] (cfg5: H 40,000 x 1,000,000, Q banded 1M^2 -> symmetric dense 40,000^2
+triple product): the largest single-GPU configuration whose metric north_star targets for multi-GPU scaling
+(cfg2 is a zero fill).  Other workloads: cfg1 cfg2 cfg3 cfg4r cfg4 (and the reduced cfg1s cfg2s cfg3s
+cfg5s cfg4r<scale>).  --impl reference times the reference's CPU implementation of the same workload (rank 0 only).
 """
 import argparse
+import ctypes
 import gc
 import json
 import os
@@ -33,6 +36,22 @@ sys.path.insert(0, ROOT)
 
 METRIC = "SpGEMM GFLOP/s (2 x intermediate products / s)"
 UNIT = "GFLOP/s"
+DEFAULT_WORKLOAD = "cfg5"
+PER_CONFIG = ("cfg1", "cfg2", "cfg3", "cfg4r", "cfg4")
+
+
+# ------------------------------------------------------------------------------------------------------
+# host threads of the CPU legs: torchrun exports OMP_NUM_THREADS=1 to its workers
+def use_all_host_threads():
+    """Make OpenMP regions use every host core and return the team size the reference routines will really get."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)            # for a libgomp not loaded yet
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1", mode=ctypes.RTLD_GLOBAL)
+        gomp.omp_set_num_threads(n)                    # for one that is (numpy / torch may have pulled it in)
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return n
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -176,13 +195,17 @@ def traffic_for(name):
         return None
 
 
+DOMINANT = {"dense": "k_dense_rows_red", "sparse": "numeric phase (k_numeric_rank + k_numeric_warp<*>)",
+            "triple": "k_triple_window"}
+
+
 # ------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own C routines (oracle/_ref) or the oracle port
-def cpu_sample(w, name, max_seconds=25.0):
+def cpu_sample(w, name, threads, max_seconds=25.0):
     """Returns (callable running one bounded sample, flops of the sample, kind, cores, description)."""
     from oracle import port, ref
     a, b, kind = w["a"], w["b"], w["kind"]
-    cores = os.cpu_count() or 1
+    cores = threads
     have_ref = ref.available()
     if kind == "dense":
         sym = bool(w["kwargs"].get("symmetric"))
@@ -227,8 +250,8 @@ def cpu_sample(w, name, max_seconds=25.0):
     return (lambda: port.triple_product(sub, b, 0)), flops, "port", 1, desc + ": oracle port, 1 thread"
 
 
-def run_reference_arm(args, w, name, info):
-    fn, flops, kind, cores, desc = cpu_sample(w, name)
+def run_reference_arm(args, w, name, info, threads):
+    fn, flops, kind, cores, desc = cpu_sample(w, name, threads)
     for _ in range(args.warmup):
         fn()
     t0 = time.perf_counter()
@@ -239,7 +262,7 @@ def run_reference_arm(args, w, name, info):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(info, sample=desc),
+            "config": dict(info, sample=desc, omp_threads=threads),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -259,183 +282,372 @@ def pinned_csr(x):
     return out
 
 
-def run_ours(args, w, name, info, flops, rank, world):
+class Resident:
+    """Operands of one workload resident in HBM, rows [r0, r1) of the product per step."""
+
+    def __init__(self, w, rank=0, world=1, torch_out=False):
+        from sparse_matrix_mult_b200 import device as dev
+        from sparse_matrix_mult_b200.matrix_ops import matrix_ops
+        self.dev, self.lib = dev, matrix_ops.get_lib()
+        a, b = w["a"], w["b"]
+        self.kind, self.sym = w["kind"], bool(w["kwargs"].get("symmetric"))
+        self.n_rows = a.shape[0]
+        self.ncols = self.n_rows if self.kind == "triple" else b.shape[1]
+        self.A = dev.DeviceMatrix.from_scipy(a)
+        self.B = self.A if (b is a) else dev.DeviceMatrix.from_scipy(b)
+        self.bounds = [0, self.n_rows]
+        if world > 1:
+            # flop-balanced partition from the GPU cost pass (the multi-GPU replacement of limits())
+            ht = self.A.transpose() if self.kind == "triple" else None
+            costs, _ = dev.row_costs(self.A, ht if ht is not None else self.B, self.B if ht is not None else None,
+                                     upper_only=(self.kind == "triple" or self.sym))
+            self.bounds = [int(x) for x in dev.partition_rows(costs, self.n_rows, world)]
+            self.lib.spgemm_b200_device_free(costs)
+            if ht is not None:
+                ht.free()
+        self.r0, self.r1 = self.bounds[rank], self.bounds[rank + 1]
+        self.out, self.out_t = None, None
+        if self.kind != "sparse":
+            if torch_out:
+                import torch
+                self.out_t = torch.empty((self.r1 - self.r0, self.ncols), dtype=torch.float64, device="cuda")
+                self.out_ptr = self.out_t.data_ptr()
+            else:
+                self.out = dev.DeviceDense(self.r1 - self.r0, self.ncols)
+                self.out_ptr = self.out.ptr
+
+    def step(self, keep=False, rows=None):
+        dev = self.dev
+        r0, r1 = rows if rows else (self.r0, self.r1)
+        if self.kind == "dense":
+            dev.spgemm_dense(self.A, self.B, self.sym, r0, r1, out=self.out_ptr)
+        elif self.kind == "sparse":
+            res = dev.spgemm_csr(self.A, self.B, self.sym, r0, r1)
+            if keep:
+                return res
+            res.free()
+        else:
+            # includes building H^T on the device (with its rows sorted) every step, at every N
+            dev.triple_product(self.A, self.B, None, True, r0, r1, out=self.out_ptr)
+        return None
+
+    def free(self):
+        if self.out is not None:
+            self.out.free()
+        self.out_t = None
+        if self.B is not self.A:
+            self.B.free()
+        self.A.free()
+
+
+def time_resident(res, steps, warm, small, barrier):
+    """-> dict(step_ms[], kernel_ms[], launches, bytes_min, stats) of `steps` timed steps after `warm` warm-ups."""
+    lib, dev = res.lib, res.dev
+    ms_c = ctypes.c_double(0.0)
+    for _ in range(warm):
+        res.step()
+    barrier()
+    step_ms, kernel_ms, launches, stats = [], [], 0, {}
+    for _ in range(steps):
+        if small:
+            lib.spgemm_b200_flush_l2()
+        barrier()
+        lib.spgemm_b200_timer_start()
+        res.step()
+        lib.spgemm_b200_timer_stop(ctypes.byref(ms_c))
+        step_ms.append(ms_c.value)
+        stats = dev.last_stats()
+        kernel_ms.append(stats["ms_numeric"])
+        launches += stats["launches"]
+    barrier()
+    return dict(step_ms=step_ms, kernel_ms=kernel_ms, launches=launches, bytes_min=stats.get("bytes_min", 0), stats=stats)
+
+
+def operands_small(a, b):
+    """Operands that could sit in the 126 MB L2 between steps: flush it (timing rules)."""
+    if os.environ.get("SPGEMM_BENCH_NO_FLUSH"):                      # experiments only
+        return False
+    return (csr_bytes(a) + csr_bytes(b)) < (256 << 20)
+
+
+L2_NOTE = {True: "flushed between timed steps (512 MB written, then 256 MB of it read back so L2 holds no dirty lines "
+                 "of the flush buffer)",
+           False: "no flush: each step streams more bytes than the 126 MB L2"}
+
+
+def e2e_single_process(w, flops, steps, warm, n_gpus):
+    """sparse_matrix_multiply(..., n_gpus=N) from pinned HOST operands to a HOST result, host wall clock."""
     from sparse_matrix_mult_b200 import device as dev
     from sparse_matrix_mult_b200 import sparse_matrix_multiply
+    from sparse_matrix_mult_b200.matrix_ops import multi_last_stats
+    a, b, kw = w["a"], w["b"], w["kwargs"]
+    ap = pinned_csr(a)
+    bp = ap if (b is a) else pinned_csr(b)
+    try:
+        t0 = time.perf_counter()
+        r = sparse_matrix_multiply(ap, bp, n_gpus=n_gpus, **kw)
+        first_ms = (time.perf_counter() - t0) * 1e3      # cold pinned-result cache, cold device pools / contexts
+        del r
+        gc.collect()
+        for _ in range(max(0, warm - 1)):
+            r = sparse_matrix_multiply(ap, bp, n_gpus=n_gpus, **kw)
+            del r
+            gc.collect()
+        e2e_ms, d2h_bytes = [], 0
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            r = sparse_matrix_multiply(ap, bp, n_gpus=n_gpus, **kw)
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+            d2h_bytes = r.nbytes if isinstance(r, np.ndarray) else (r.data.nbytes + r.indices.nbytes + r.indptr.nbytes)
+            del r
+            gc.collect()            # outside the timed region: result storage goes back to the pinned cache
+        e2e_t = float(np.mean(e2e_ms))
+        if n_gpus > 1:
+            per = multi_last_stats()
+            h2d = sum(int(s["bytes_h2d"]) for s in per)
+            d2h = sum(int(s["bytes_d2h"]) for s in per) or d2h_bytes
+            device_ms = {k: round(max(s[k] for s in per), 3) for k in
+                         ("ms_h2d", "ms_analysis", "ms_symbolic", "ms_numeric", "ms_post", "ms_d2h", "ms_total")}
+        else:
+            st = dev.last_stats()           # of the last end-to-end call: bytes that actually crossed PCIe
+            h2d, d2h = int(st["bytes_h2d"]), int(st["bytes_d2h"])
+            device_ms = {k: round(st[k], 3) for k in ("ms_h2d", "ms_analysis", "ms_symbolic", "ms_numeric", "ms_post",
+                                                      "ms_d2h", "ms_total")}
+        return {"value": flops / (e2e_t * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_t, "first_call_ms": first_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "result_bytes": int(d2h_bytes),
+                "device_ms": device_ms, "n_gpus": n_gpus,
+                "path": "sparse_matrix_multiply(n_gpus=%d): one host thread per GPU inside the library, every GPU "
+                        "uploads over its own PCIe link and writes its rows of the host result" % n_gpus if n_gpus > 1
+                        else "sparse_matrix_multiply()",
+                "timing": "host wall clock around the call"}
+    except OverflowError as ex:       # nnz(C) >= 2^31 cannot be returned as a SciPy int32 CSR (BASELINE cfg4)
+        return {"value": None, "unit": UNIT, "unavailable": str(ex)}
+    finally:
+        del ap, bp
+        gc.collect()
+
+
+def roofline_of(kind, name, t, peak, peak_src):
+    k_ms = float(np.mean(t["kernel_ms"]))
+    achieved = (t["bytes_min"] / 1e9) / (k_ms * 1e-3) if k_ms > 0 else 0.0
+    return {"bound": "hbm", "kernel": DOMINANT[kind], "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic_for(name), "algorithmic_bytes": int(t["bytes_min"]),
+            "kernel_ms": k_ms, "peak_source": peak_src}
+
+
+def run_per_config(names, steps, peak, peak_src, lib):
+    """value / roofline / e2e of the other BASELINE configs on one GPU (short runs: each step is < 1 s of GPU time)."""
+    from sparse_matrix_mult_b200 import synthetic
+    out = {}
+    for name in names:
+        t_setup = time.perf_counter()
+        try:
+            w = synthetic.workload(name)
+            info, flops = describe(w, name)
+            res = Resident(w)
+            small = operands_small(w["a"], w["b"])
+            t = time_resident(res, steps, 3, small, lib.spgemm_b200_synchronize)
+            res.free()
+            ms = float(np.mean(t["step_ms"]))
+            entry = {"value": flops / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": 3,
+                     "flops": int(flops), "roofline": roofline_of(w["kind"], name, t, peak, peak_src),
+                     "phases_ms": {k: round(t["stats"].get(k, 0.0), 4) for k in
+                                   ("ms_analysis", "ms_symbolic", "ms_numeric", "ms_post")},
+                     "nnz_c": int(t["stats"].get("nnz_c", 0)), "gpu_launches": int(t["launches"]),
+                     "l2": L2_NOTE[small]}
+            if name == "cfg4":
+                entry["e2e"] = {"value": None, "unit": UNIT,
+                                "unavailable": "nnz(C) = 9.7e9 does not fit SciPy's int32 CSR (nor the reference's)"}
+            else:
+                entry["e2e"] = e2e_single_process(w, flops, max(2, steps // 2), 1, 1)
+            lib.spgemm_b200_trim(0)
+            del w
+            gc.collect()
+        except Exception as ex:                # noqa: BLE001 -- a side entry must not lose the headline line
+            entry = {"error": repr(ex)}
+        entry["setup_s"] = round(time.perf_counter() - t_setup, 1)
+        out[name] = entry
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# N > 1: checksums of every rank's row block against the same rows of a one-GPU run on rank 0
+def block_checksums(kind, res, rows, torch):
+    """(count, sum, column-weighted sum, sum of squares) of rows [r0, r1) computed by THIS rank."""
+    lib, dev = res.lib, res.dev
+    if kind == "sparse":
+        h = res.step(keep=True, rows=rows)
+        p, i, v = h.device_ptrs()
+        idx = torch.empty(max(1, h.nnz), dtype=torch.int32, device="cuda")
+        val = torch.zeros(max(1, h.nnz), dtype=torch.float64, device="cuda")
+        if h.nnz:
+            dev.copy_on_device(idx.data_ptr(), i, h.nnz * 4)
+            dev.copy_on_device(val.data_ptr(), v, h.nnz * 8)
+        lib.spgemm_b200_synchronize()
+        nnz = h.nnz
+        h.free()
+        if not nnz:
+            return [0.0, 0.0, 0.0, 0.0]
+        wgt = torch.cos(idx[:nnz].to(torch.float64) * 1e-3)
+        return [float(nnz), float(val[:nnz].sum()), float((val[:nnz] * wgt).sum()), float((val[:nnz] ** 2).sum())]
+    r0, r1 = rows
+    out = torch.empty((r1 - r0, res.ncols), dtype=torch.float64, device="cuda")
+    if r1 > r0:
+        if kind == "dense":
+            dev.spgemm_dense(res.A, res.B, res.sym, r0, r1, out=out.data_ptr())
+        else:
+            dev.triple_product(res.A, res.B, None, True, r0, r1, out=out.data_ptr())
+    lib.spgemm_b200_synchronize()
+    wgt = torch.cos(torch.arange(res.ncols, device="cuda", dtype=torch.float64) * 1e-3)
+    return [float(torch.count_nonzero(out)), float(out.sum()), float((out * wgt).sum()), float((out ** 2).sum())]
+
+
+def multi_gpu_parity(res, rank, world, dist, torch):
+    """Every rank checksums its own block; rank 0 recomputes every block alone and compares."""
+    mine = torch.tensor(block_checksums(res.kind, res, (res.r0, res.r1), torch), device="cuda", dtype=torch.float64)
+    allc = [torch.zeros(4, device="cuda", dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(allc, mine)
+    if rank != 0:
+        return None
+    worst, ok = 0.0, True
+    for r in range(world):
+        ref = block_checksums(res.kind, res, (res.bounds[r], res.bounds[r + 1]), torch)
+        got = [float(x) for x in allc[r].tolist()]
+        ok = ok and got[0] == ref[0]
+        for g, w in zip(got[1:], ref[1:]):
+            rel = abs(g - w) / max(abs(w), 1e-300)
+            worst = max(worst, rel)
+    ok = ok and worst < 1e-9
+    return {"ok": bool(ok), "max_rel_diff": worst,
+            "what": "per-rank row block (non-zero count, sum, cos-weighted sum, sum of squares) vs the same rows "
+                    "computed by rank 0 alone"}
+
+
+def run_ours(args, w, name, info, flops, rank, world, threads):
+    from sparse_matrix_mult_b200 import device as dev
     from sparse_matrix_mult_b200.matrix_ops import matrix_ops
 
     lib = matrix_ops.get_lib()
     local = int(os.environ.get("LOCAL_RANK", 0))
     dev.init(local)
-    dist = None
+    dist, torch, cpu_group = None, None, None
     if world > 1:
         import torch
-        import torch.distributed as dist_mod
+        import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # host-side waits go through gloo: an NCCL barrier would park a spinning kernel on every GPU while rank 0's
+        # end-to-end leg is using them
+        cpu_group = dist.new_group(backend="gloo")
         box = [info, flops]
         dist.broadcast_object_list(box, src=0)
         info, flops = box
 
-    a, b, kind, kw = w["a"], w["b"], w["kind"], w["kwargs"]
-    sym = bool(kw.get("symmetric"))
-    n_rows = a.shape[0]
-
-    # ---- operands resident in HBM; rows sharded by the flop-balanced partition for N > 1 -------------
-    A = dev.DeviceMatrix.from_scipy(a)
-    B = A if (b is a) else dev.DeviceMatrix.from_scipy(b)
-    Ht = A.transpose() if kind == "triple" else None
-    if world > 1:
-        costs, _ = dev.row_costs(A, Ht if kind == "triple" else B, B if kind == "triple" else None,
-                                 upper_only=(kind == "triple" or sym))
-        bounds = dev.partition_rows(costs, n_rows, world)
-        lib.spgemm_b200_device_free(costs)
-        r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
-    else:
-        r0, r1 = 0, n_rows
-    out = None
-    if kind == "dense":
-        out = dev.DeviceDense(r1 - r0, b.shape[1])
-    elif kind == "triple":
-        out = dev.DeviceDense(r1 - r0, n_rows)
-
-    def step_device():
-        if kind == "dense":
-            dev.spgemm_dense(A, B, sym, r0, r1, out=out)
-        elif kind == "sparse":
-            dev.spgemm_csr(A, B, sym, r0, r1).free()
-        else:
-            dev.triple_product(A, B, None, True, r0, r1, out=out)      # includes building H^T on the device
-
-    small = (csr_bytes(a) + csr_bytes(b)) < (256 << 20)               # operands could sit in the 126 MB L2
-    if os.environ.get("SPGEMM_BENCH_NO_FLUSH"):                      # experiments only
-        small = False
-    ms_c = ctypes_double()
+    a, b, kind = w["a"], w["b"], w["kind"]
+    res = Resident(w, rank, world)
+    small = operands_small(a, b)
 
     def barrier():
         lib.spgemm_b200_synchronize()
         if dist:
-            dist.barrier()
+            dist.barrier(group=cpu_group)
 
     n_warm = max(3, args.warmup)                                    # timing rules: at least 3 warm-up steps
-    for _ in range(n_warm):
-        step_device()
-    barrier()
-    kernel_ms, step_ms, launches, bytes_min, last_stats = [], [], 0, 0, {}
     # clocks / throttle reasons are sampled from here to the end of the end-to-end leg (the resident leg alone
     # lasts a few milliseconds: too short for nvidia-smi's sampling period)
     clocks = ClockSampler(local)
     clocks.__enter__()
-    for _ in range(args.steps):
-        if small:
-            lib.spgemm_b200_flush_l2()
-        barrier()
-        lib.spgemm_b200_timer_start()
-        step_device()
-        lib.spgemm_b200_timer_stop(ms_c)
-        step_ms.append(ms_c.value)
-        st = dev.last_stats()
-        last_stats = st
-        kernel_ms.append(st["ms_numeric"])
-        launches += st["launches"]
-        bytes_min = st["bytes_min"]
-    barrier()
-    t_local = float(np.sum(step_ms))
+    t = time_resident(res, args.steps, n_warm, small, barrier)
+    t_local = float(np.sum(t["step_ms"]))
+    launches, bytes_min = t["launches"], t["bytes_min"]
+    rank_ms, parity = None, None
     if dist:
-        import torch
-        t = torch.tensor([t_local], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_job = float(t.item())
-        bm = torch.tensor([float(bytes_min), float(launches)], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([t_local], device="cuda", dtype=torch.float64)
+        every = [torch.zeros(1, device="cuda", dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(every, tt)
+        rank_ms = [float(x.item()) / args.steps for x in every]
+        t_job = max(rank_ms) * args.steps
+        bm = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
         dist.all_reduce(bm)
-        bytes_min_job, launches = float(bm[0].item()), int(bm[1].item())
+        launches = int(bm[0].item())
+        parity = multi_gpu_parity(res, rank, world, dist, torch)
     else:
-        t_job, bytes_min_job = t_local, float(bytes_min)
+        t_job = t_local
     ms_per_step = t_job / args.steps
     value = flops / (ms_per_step * 1e-3) / 1e9
 
     # ---- end to end through the public API (host operands in pinned memory, host result) ---------------
     e2e = None
-    if args.no_e2e:
-        pass
-    elif world == 1:
-        ap = pinned_csr(a)
-        bp = ap if (b is a) else pinned_csr(b)
-        try:
-            for _ in range(min(2, args.warmup)):
-                r = sparse_matrix_multiply(ap, bp, **kw)
-                del r
-                gc.collect()
-            e2e_ms, d2h_bytes = [], 0
-            for _ in range(args.steps):
-                t0 = time.perf_counter()
-                r = sparse_matrix_multiply(ap, bp, **kw)
-                e2e_ms.append((time.perf_counter() - t0) * 1e3)
-                d2h_bytes = r.nbytes if isinstance(r, np.ndarray) else (r.data.nbytes + r.indices.nbytes + r.indptr.nbytes)
-                del r
-                gc.collect()            # outside the timed region: result storage goes back to the pinned cache
-            e2e_t = float(np.mean(e2e_ms))
-            st = dev.last_stats()           # of the last end-to-end call: bytes that actually crossed PCIe
-            e2e = {"value": flops / (e2e_t * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_t,
-                   "h2d_bytes_per_step": int(st["bytes_h2d"]), "d2h_bytes_per_step": int(st["bytes_d2h"]),
-                   "result_bytes": int(d2h_bytes),
-                   "device_ms": {k: round(st[k], 3) for k in ("ms_h2d", "ms_analysis", "ms_symbolic", "ms_numeric",
-                                                               "ms_post", "ms_d2h", "ms_total")},
-                   "timing": "host wall clock around sparse_matrix_multiply()"}
-        except OverflowError as ex:       # nnz(C) >= 2^31 cannot be returned as a SciPy int32 CSR (BASELINE cfg4)
-            e2e = {"value": None, "unit": UNIT, "unavailable": str(ex)}
-    else:
-        from sparse_matrix_mult_b200 import distributed as sd
-        e2e = sd.bench_e2e(args, w, flops, rank, world, csr_bytes)
+    if not args.no_e2e:
+        if world == 1:
+            e2e = e2e_single_process(w, flops, args.steps, min(2, args.warmup), 1)
+        elif args.e2e_mode == "nccl":
+            from sparse_matrix_mult_b200 import distributed as sd
+            e2e = sd.bench_e2e(args, w, flops, rank, world, csr_bytes)
+        else:
+            # rank 0 drives all N GPUs through the drop-in API; the other ranks keep their GPUs idle and wait on CPU
+            barrier()
+            if rank == 0:
+                e2e = e2e_single_process(w, flops, args.steps, min(2, args.warmup), world)
+            barrier()
 
     clocks.__exit__(None, None, None)
+    res.free()
     if dist:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peak()
-    k_ms = float(np.mean(kernel_ms))
-    achieved = (bytes_min / 1e9) / (k_ms * 1e-3) if k_ms > 0 else 0.0
-    dominant = {"dense": "k_dense_rows_red", "sparse": "numeric phase (k_numeric_rank + k_numeric_warp<*>)",
-                "triple": "k_triple_rows_red"}[kind]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(info, parallelism=f"rows sharded over {world} GPU(s), flop-balanced",
-                           l2="flushed between timed steps (512 MB written, then 256 MB of it read back so L2 holds no "
-                              "dirty lines of the flush buffer)" if small else
-                              "no flush: each step streams more bytes than the 126 MB L2"),
+            "config": dict(info, parallelism=f"rows sharded over {world} GPU(s), flop-balanced", l2=L2_NOTE[small],
+                           step="H^T is rebuilt on the device inside every timed step" if kind == "triple" else
+                                "analysis + symbolic + numeric phases" if kind == "sparse" else "one kernel"),
             "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic_for(name),
-                         "algorithmic_bytes": int(bytes_min), "kernel_ms": k_ms, "peak_source": peak_src},
-            "phases_ms": {k: round(last_stats.get(k, 0.0), 4) for k in
+            "roofline": roofline_of(kind, name, t, peak, peak_src),
+            "phases_ms": {k: round(t["stats"].get(k, 0.0), 4) for k in
                           ("ms_analysis", "ms_symbolic", "ms_numeric", "ms_post")},
-            "nnz_c": int(last_stats.get("nnz_c", 0)),
+            "nnz_c": int(t["stats"].get("nnz_c", 0)),
             "clocks": dict(clocks.summary(), window="timed steps of the resident leg + the end-to-end leg")}
+    if world > 1:
+        mean = float(np.mean(rank_ms))
+        line["parity"] = parity
+        line["residual"] = {"rank_ms": [round(x, 4) for x in rank_ms], "bounds": res.bounds,
+                            "imbalance_max_over_mean": max(rank_ms) / mean if mean > 0 else None,
+                            "rank0_fixed_ms": round(t["stats"].get("ms_analysis", 0.0), 4),
+                            "note": "rank_ms = mean CUDA-event time of a step on each rank; rank0_fixed_ms = part of "
+                                    "rank 0's step that does not shrink with N (H^T build / analysis)"}
     # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------
     if world == 1 and not args.no_cpu:
-        fn, cflops, ckind, cores, desc = cpu_sample(w, name)
+        fn, cflops, ckind, cores, desc = cpu_sample(w, name, threads)
+        t0 = time.perf_counter()
+        fn()                                   # first call: page faults of the result, thread team start-up
+        first = time.perf_counter() - t0
         t0 = time.perf_counter()
         fn()
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": cflops / dt / 1e9, "unit": UNIT, "cores": cores, "kind": ckind,
-                                "sample": desc, "seconds": dt}
+                                "sample": desc, "seconds": dt, "first_call_seconds": first}
         if kind == "sparse":
             # the reference has no working multi-threaded sparse path (SURVEY.md 0.3); for scale, the oracle's
             # OpenMP port of it (bit-identical rows, dynamic row blocks) on every host core
             from oracle import port
-            ncores = os.cpu_count() or 1
+            sym = bool(w["kwargs"].get("symmetric"))
             sub = a if "full" in desc else a[:int(desc.split("[0,")[1].split(")")[0])]
-            port.spgemm_csr(sub, b, sym, omp_blocks=16 * ncores, copy=False)          # warm-up (threads, pages)
+            port.spgemm_csr(sub, b, sym, omp_blocks=16 * threads, copy=False)          # warm-up (threads, pages)
             t0 = time.perf_counter()
-            port.spgemm_csr(sub, b, sym, omp_blocks=16 * ncores, copy=False)
+            port.spgemm_csr(sub, b, sym, omp_blocks=16 * threads, copy=False)
             dt = time.perf_counter() - t0
-            line["cpu_baseline_omp_port"] = {"value": cflops / dt / 1e9, "unit": UNIT, "cores": ncores, "kind": "port",
+            line["cpu_baseline_omp_port"] = {"value": cflops / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
                                              "sample": desc.split(":")[0] + ": oracle_spgemm_csr_omp, C call only",
                                              "seconds": dt}
+    if world == 1 and name == DEFAULT_WORKLOAD and not args.no_per_config:
+        del w, a, b
+        gc.collect()
+        lib.spgemm_b200_trim(0)
+        line["per_config"] = run_per_config(PER_CONFIG, max(3, min(5, args.steps)), peak, peak_src, lib)
     emit(line)
 
 
@@ -451,20 +663,19 @@ def emit(line):
         sys.stdout.flush()
 
 
-def ctypes_double():
-    import ctypes
-    return ctypes.c_double(0.0)
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-per-config", action="store_true", help="skip the per_config block of the default run")
+    ap.add_argument("--e2e-mode", default="api", choices=["api", "nccl"],
+                    help="N > 1 end-to-end leg: the drop-in API with n_gpus=N on rank 0 (default) or the "
+                         "one-process-per-GPU NCCL broadcast/gather path of distributed.py")
     ap.add_argument("--recount", action="store_true", help="recount products on the host even if cached")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -476,6 +687,7 @@ def main():
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
+    threads = use_all_host_threads() if (rank == 0) else 1
 
     from sparse_matrix_mult_b200 import synthetic
     w = synthetic.workload(args.workload)
@@ -484,9 +696,9 @@ def main():
     else:
         info, flops = None, None
     if args.impl == "reference":
-        run_reference_arm(args, w, args.workload, info)
+        run_reference_arm(args, w, args.workload, info, threads)
     else:
-        run_ours(args, w, args.workload, info, flops, rank, world)
+        run_ours(args, w, args.workload, info, flops, rank, world, threads)
     return 0
 
 

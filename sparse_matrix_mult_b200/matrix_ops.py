@@ -323,7 +323,8 @@ def sparse_matrix_multiply(matrix_a, matrix_b, output_format='sparse', symmetric
     n_gpus = _default_gpus() if n_gpus is None else int(n_gpus)
     if n_gpus < 1:
         raise ValueError("n_gpus must be a positive integer")
-    if n_gpus > 1 and not (mirror or (use_triple_product and compute_full_matrix)):
+    force_multi = bool(os.environ.get("SPGEMM_B200_FORCE_MULTI"))        # tests: multi-GPU driver on a one-GPU box
+    if (n_gpus > 1 or force_multi) and not (mirror or (use_triple_product and compute_full_matrix)):
         return _multiply_multi(lib, n_gpus, a_arr, b_arr, (m, k, n), output_format, symmetric, use_triple_product)
     if use_triple_product:
         # like the reference (matrix_ops.py:312-313 is the only check) Q is assumed square with H.cols rows;

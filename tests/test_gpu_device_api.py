@@ -1,0 +1,291 @@
+"""GPU tests of the entry points beside the host-buffer API:
+  * the device-resident row-range calls (spgemm_b200_*_dev) that bench.py's `value` and the multi-GPU paths time:
+    disjoint row ranges stitched and compared with the oracle (global row numbers in the col >= row cut);
+  * upper_only through the block-bin (bitmap / rank) kernels;
+  * n_gpus= through the public API (single-process multi-GPU driver; runs with n_gpus=1 on a one-GPU box and
+    with every available count up to 8 otherwise);
+  * thread safety of concurrent calls, operand validation, device-side canonicalisation of an unsorted B.
+"""
+import threading
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import cases
+from helpers import assert_csr_equal, assert_dense_equal
+from oracle import port
+from sparse_matrix_mult_b200 import device as dev
+from sparse_matrix_mult_b200 import sparse_matrix_multiply, synthetic
+from sparse_matrix_mult_b200.matrix_ops import matrix_ops, multi_last_bounds, multi_last_stats
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpus():
+    return matrix_ops.get_lib().spgemm_b200_device_count()
+
+
+def _ranges(n):
+    cuts = [0, n // 5, n // 5, (2 * n) // 3, n]          # includes an empty range
+    return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
+
+
+# ---- device API, row ranges ------------------------------------------------------------------------------
+@pytest.mark.parametrize("upper", [False, True])
+def test_device_csr_row_ranges(upper):
+    a, b = cases.seeded_pair(700, 0.02)
+    A, B = dev.DeviceMatrix.from_scipy(a), dev.DeviceMatrix.from_scipy(b)
+    want = port.spgemm_csr(a, b, upper)
+    blocks = []
+    for r0, r1 in _ranges(a.shape[0]):
+        res = dev.spgemm_csr(A, B, upper, r0, r1)
+        assert res.shape == (r1 - r0, b.shape[1])
+        blocks.append(res.to_scipy() if res.nnz else sp.csr_matrix((r1 - r0, b.shape[1])))
+        res.free()
+    assert_csr_equal(sp.vstack(blocks).tocsr(), want, f"csr_dev ranges upper={upper}")
+    # row_begin with row_end=None means "to the last row" (device._rows ignored row_begin)
+    tail = dev.spgemm_csr(A, B, upper, 500)
+    assert tail.shape[0] == 200
+    want.sort_indices()
+    assert_csr_equal(tail.to_scipy(), want[500:], "csr_dev tail")
+    tail.free()
+
+
+@pytest.mark.parametrize("upper", [False, True])
+def test_device_dense_row_ranges(upper):
+    a, b = cases.seeded_pair(600, 0.03)
+    A, B = dev.DeviceMatrix.from_scipy(a), dev.DeviceMatrix.from_scipy(b)
+    want = port.spgemm_dense(a, b, upper)
+    got = np.empty_like(want)
+    for r0, r1 in _ranges(a.shape[0]):
+        if r1 == r0:
+            continue
+        out = dev.spgemm_dense(A, B, upper, r0, r1)
+        got[r0:r1] = out.to_host()
+        out.free()
+    assert_dense_equal(got, want, f"dense_dev ranges upper={upper}")
+
+
+@pytest.mark.parametrize("name", ["cfg3s", "cfg5s"])
+@pytest.mark.parametrize("upper", [True, False])
+def test_device_triple_row_ranges(name, upper):
+    w = synthetic.workload(name)
+    h, q = w["a"], w["b"]
+    H, Q = dev.DeviceMatrix.from_scipy(h), dev.DeviceMatrix.from_scipy(q)
+    Ht = H.transpose()
+    n = h.shape[0]
+    if upper:
+        want = port.triple_product(h, q, 0)
+    else:
+        want = (h @ q @ h.T).toarray()
+    got = np.empty((n, n))
+    for k, (r0, r1) in enumerate(_ranges(n)):
+        if r1 == r0:
+            continue
+        out = dev.triple_product(H, Q, Ht if k % 2 == 0 else None, upper, r0, r1)     # with and without a cached H^T
+        got[r0:r1] = out.to_host()
+        out.free()
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14, err_msg=f"triple_dev ranges {name} upper={upper}")
+    if upper:
+        assert not np.tril(got, -1).any()
+
+
+def test_triple_wide_output_overflows_the_shared_window():
+    """n = 30,000 output columns: rows near the top are wider than the shared-memory window (~26,800 doubles), so
+    their far columns take the L2-reduction path; rows further down fit.  Checked on sampled rows against SciPy."""
+    rng = np.random.default_rng(12)
+    n, k = 30_000, 120_000
+    h = sp.random(n, k, density=3.0 / k, format='csr', random_state=rng)
+    q = synthetic.banded_cov(k, half_width=3, length=2.0)
+    H, Q = dev.DeviceMatrix.from_scipy(h), dev.DeviceMatrix.from_scipy(q)
+    hq = (h @ q).tocsr()
+    for r0, r1 in [(0, 40), (2_000, 2_030), (29_950, 30_000)]:
+        out = dev.triple_product(H, Q, None, True, r0, r1)
+        got = out.to_host()
+        out.free()
+        want = (hq[r0:r1] @ h.T).toarray()
+        for i in range(r0, r1):
+            np.testing.assert_allclose(got[i - r0, i:], want[i - r0, i:], rtol=1e-12, atol=1e-14)
+            assert not got[i - r0, :i].any()
+
+
+def test_triple_long_rows_of_ht():
+    """H with a few dense columns: rows of H^T far longer than the per-thread sort limit (block bitonic sort) and
+    than the sub-warp groups of the contraction."""
+    rng = np.random.default_rng(3)
+    n, k = 900, 400
+    h = sp.random(n, k, density=0.01, format='csr', random_state=rng).tolil()
+    h[:, 7] = rng.random((n, 1))
+    h[::2, 123] = rng.random((n // 2, 1))
+    h = h.tocsr()
+    q = cases.banded(k, 3)
+    got = sparse_matrix_multiply(h, q, use_triple_product=True)
+    assert_dense_equal(got, port.triple_product(h, q, 0), "long H^T rows")
+    full = sparse_matrix_multiply(h, q, use_triple_product=True, compute_full_matrix=1)
+    assert_dense_equal(full, port.triple_product(h, q, 1), "long H^T rows, reference full mode")
+
+
+# ---- upper_only through the block-bin kernels -----------------------------------------------------------------
+def test_symmetric_sparse_heavy_rows():
+    """Rows with > 768 entries take k_symbolic_bitmap / k_numeric_rank; symmetric=True runs them with the column
+    window [row, n)."""
+    rng = np.random.default_rng(21)
+    n = 3000
+    a = sp.random(n, n, density=0.02, format='csr', random_state=rng)
+    b = sp.random(n, n, density=0.02, format='csr', random_state=rng)
+    got = sparse_matrix_multiply(a, b, symmetric=True)
+    want = port.spgemm_csr(a, b, True)
+    assert np.diff(want.indptr).max() > 768
+    assert_csr_equal(got, want, "symmetric heavy rows")
+    # wide matrix: compact rank table (> 419k columns) with the upper-triangle window
+    n = 600_000
+    b = sp.random(n, n, density=2.5 / n, format='csr', random_state=rng)
+    rows, cols = [], []
+    for i, c in enumerate([0, 3, 400, 1500, 5000, 900, 2500]):
+        rows += [i * 50_000] * c
+        cols += list(rng.choice(n, size=c, replace=False))
+    a = sp.csr_matrix((rng.random(len(rows)), (rows, cols)), shape=(n, n))
+    got = sparse_matrix_multiply(a, b, symmetric=True)
+    want = port.spgemm_csr(a, b, True)
+    assert np.diff(want.indptr).max() > 768
+    assert_csr_equal(got, want, "symmetric heavy rows, wide")
+
+
+# ---- n_gpus through the public API -------------------------------------------------------------------------
+def _gpu_counts():
+    n = _gpus()
+    return [c for c in (1, 2, 3, 4, 8) if c <= max(1, n)]
+
+
+@pytest.mark.parametrize("name", ["cfg1s", "cfg2s", "cfg3s", "cfg4r10", "cfg5s"])
+def test_multi_gpu_public_api(name, monkeypatch):
+    monkeypatch.setenv("SPGEMM_B200_FORCE_MULTI", "1")     # n_gpus=1 also goes through the multi-GPU driver
+    w = synthetic.workload(name)
+    want = port.sparse_matrix_multiply(w["a"], w["b"], **w["kwargs"])
+    for n_gpus in _gpu_counts():
+        got = sparse_matrix_multiply(w["a"], w["b"], n_gpus=n_gpus, **w["kwargs"])
+        if w["kind"] == "sparse":
+            assert_csr_equal(got, want, f"{name} n_gpus={n_gpus}")
+        else:
+            assert_dense_equal(got, want, f"{name} n_gpus={n_gpus}")
+        bounds = multi_last_bounds()
+        assert len(bounds) == n_gpus + 1 and bounds[0] == 0 and bounds[-1] == w["a"].shape[0]
+        assert all(bounds[i] <= bounds[i + 1] for i in range(n_gpus))
+        assert len(multi_last_stats()) == n_gpus
+
+
+def test_multi_gpu_symmetric_and_rectangular(monkeypatch):
+    monkeypatch.setenv("SPGEMM_B200_FORCE_MULTI", "1")
+    a, b = cases.seeded_pair(500, 0.05)
+    r = sp.random(300, 500, density=0.05, format='csr', random_state=np.random.default_rng(2))
+    for n_gpus in _gpu_counts():
+        assert_csr_equal(sparse_matrix_multiply(a, b, symmetric=True, n_gpus=n_gpus), port.spgemm_csr(a, b, True), "sym sparse")
+        assert_dense_equal(sparse_matrix_multiply(a, b, output_format='dense', n_gpus=n_gpus), port.spgemm_dense(a, b), "dense")
+        assert_dense_equal(sparse_matrix_multiply(r, b, output_format='dense', n_gpus=n_gpus), port.spgemm_dense(r, b), "rect dense")
+        assert_csr_equal(sparse_matrix_multiply(r, b, n_gpus=n_gpus), port.spgemm_csr(r, b), "rect sparse")
+        # modes that need the whole matrix fall back to one GPU and still honour their contract
+        t1 = sparse_matrix_multiply(a, cases.banded(500), use_triple_product=True, compute_full_matrix=1, n_gpus=n_gpus)
+        assert_dense_equal(t1, port.triple_product(a, cases.banded(500), 1), "triple1")
+    with pytest.raises(RuntimeError, match="GPUs"):
+        sparse_matrix_multiply(a, b, n_gpus=_gpus() + 1)
+
+
+# ---- thread safety ----------------------------------------------------------------------------------------------
+def test_concurrent_calls_from_python_threads():
+    """ctypes.CDLL releases the GIL: two threads really are inside the library at once (api.cu global
+    context).  Each thread multiplies its own pair many times and must always get its own answer."""
+    pairs = [cases.seeded_pair(300 + 40 * t, 0.05) for t in range(4)]
+    wants = [(port.spgemm_csr(a, b), port.spgemm_dense(a, b, True)) for a, b in pairs]
+    errors = []
+
+    def work(t):
+        try:
+            a, b = pairs[t]
+            for _ in range(15):
+                assert_csr_equal(sparse_matrix_multiply(a, b), wants[t][0], f"thread {t} sparse")
+                assert_dense_equal(sparse_matrix_multiply(a, b, output_format='dense', symmetric=True), wants[t][1],
+                                   f"thread {t} dense")
+        except Exception as ex:          # noqa: BLE001
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:3]
+
+
+# ---- validation and canonicalisation -------------------------------------------------------------------------------
+def test_invalid_operands_are_rejected_before_any_kernel_reads_them():
+    a, b = cases.seeded_pair(200, 0.05)
+    bad = b.copy()
+    bad.indices = bad.indices.copy()
+    bad.indices[17] = b.shape[1] + 5                      # column index out of range
+    for kw in (dict(), dict(output_format='dense'), dict(use_triple_product=True)):
+        with pytest.raises(RuntimeError, match="out of range|monotone"):
+            sparse_matrix_multiply(a, bad, **kw)
+    bad = a.copy()
+    bad.indices = bad.indices.copy()
+    bad.indices[3] = -2
+    with pytest.raises(RuntimeError, match="out of range|monotone"):
+        sparse_matrix_multiply(bad, b)
+    bad = b.copy()
+    bad.indptr = bad.indptr.copy()
+    bad.indptr[5] = bad.indptr[4] - 1                     # row 4 ends before it starts
+    assert (np.diff(bad.indptr) < 0).any()
+    with pytest.raises(RuntimeError, match="out of range|monotone"):
+        sparse_matrix_multiply(a, bad)
+    # the context is still healthy afterwards
+    assert_csr_equal(sparse_matrix_multiply(a, b), port.spgemm_csr(a, b), "after rejected operands")
+
+
+def test_unsorted_b_is_canonicalised_on_the_device():
+    rng = np.random.default_rng(8)
+    n = 5_000
+    b0 = sp.random(n, n, density=4e-3, format='csr', random_state=rng)
+    idx, val = b0.indices.copy(), b0.data.copy()
+    for r in range(n):                                    # reversed rows; every 7th row also gets a duplicate entry
+        s, e = b0.indptr[r], b0.indptr[r + 1]
+        idx[s:e], val[s:e] = idx[s:e][::-1], val[s:e][::-1]
+        if r % 7 == 0 and e - s >= 2:
+            idx[s] = idx[e - 1]
+    b = sp.csr_matrix((n, n))
+    b.indptr, b.indices, b.data = b0.indptr, idx, val
+    a = sp.random(n, n, density=2e-3, format='csr', random_state=rng)
+    A, B = dev.DeviceMatrix.from_scipy(a), dev.DeviceMatrix.from_scipy(b)
+    assert not B.is_sorted() and A.is_sorted()
+    res = dev.spgemm_csr(A, B, True)                      # windowed (upper_only): wants binary search in B's rows
+    assert_csr_equal(res.to_scipy(), port.spgemm_csr(a, b, True), "unsorted B, device API")
+    res.free()
+    assert B.is_sorted()                                   # sorted in place on the device: no filter fallback left
+    out = dev.spgemm_dense(A, B, True)
+    assert_dense_equal(out.to_host(), port.spgemm_dense(a, b, True), "unsorted B dense")
+    out.free()
+    # borrowed arrays are never modified: a sorted shadow copy is used instead
+    import ctypes
+    lib = matrix_ops.get_lib()
+    arrs = [np.ascontiguousarray(x) for x in (b.indptr.astype(np.int32), b.indices.astype(np.int32), b.data)]
+    ptrs = []
+    for x in arrs:
+        p = lib.spgemm_b200_device_alloc(x.nbytes)
+        lib.spgemm_b200_copy_to_device(ctypes.c_void_p(p), x.ctypes.data_as(ctypes.c_void_p), x.nbytes)
+        ptrs.append(p)
+    W = dev.DeviceMatrix.wrap(b.shape, b.nnz, *ptrs)
+    res = dev.spgemm_csr(A, W, True)
+    assert_csr_equal(res.to_scipy(), port.spgemm_csr(a, b, True), "unsorted borrowed B")
+    res.free()
+    back = np.empty_like(arrs[1])
+    lib.spgemm_b200_copy_to_host(back.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(ptrs[1]), back.nbytes)
+    assert np.array_equal(back, arrs[1])                   # the caller's indices are untouched
+    W.free()
+    for p in ptrs:
+        lib.spgemm_b200_device_free(ctypes.c_void_p(p))
+
+
+def test_trim_releases_cached_memory():
+    a, b = cases.seeded_pair(400, 0.05)
+    sparse_matrix_multiply(a, b, output_format='dense')
+    assert matrix_ops.get_lib().spgemm_b200_trim(0) == 0
+    assert_dense_equal(sparse_matrix_multiply(a, b, output_format='dense'), port.spgemm_dense(a, b), "after trim")
