@@ -616,7 +616,9 @@ int csr_impl(spgemm_b200_mat* a, spgemm_b200_mat* b_in, int upper_only, int r0, 
         e = launch_symbolic(lc, job, d_lists, sym_counts, d_nnz, d_work);
         if (e == cudaSuccess) e = launch_scan_i64(lc, d_nnz, res->d_ptr, m, scan_tmp);
         if (e == cudaSuccess) e = cudaMemsetAsync(d_cursor, 0, 16 * sizeof(int32_t), g.stream);
-        if (e == cudaSuccess) e = launch_bin_by_nnz(lc, d_nnz, m, d_lists, d_cursor);
+        int cap_h4k = 0, cap_h12k = 0;
+        numeric_hash_caps(n, &cap_h4k, &cap_h12k);
+        if (e == cudaSuccess) e = launch_bin_by_nnz(lc, d_nnz, m, d_lists, d_cursor, cap_h4k, cap_h12k);
         if (e != cudaSuccess) return bail(fail(SPGEMM_B200_ERR_CUDA, "symbolic phase", e));
         mark(EV_SYMBOLIC);
     }

@@ -60,156 +60,169 @@ __device__ __forceinline__ void triple_flush_counters(unsigned long long p1, uns
 // ---------------------------------------------------------------------------------------------------
 // Shared-memory window kernel.
 //
-// Per row i (rows handed out in order through an atomic ticket: upper-triangle rows get cheaper towards the
-// bottom, so in-order dynamic scheduling is longest-first):
+// Per row i of C:
 //   1. up to blockDim entries (j, h_ij) of H[i,:] are loaded one per thread together with the extent of row j of Q;
 //      a block-wide prefix sum numbers the products of the expansion 0..total-1;
-//   2. the product range is cut into equal contiguous shares, one per warp: lane l of a warp takes product
-//      f0 + l, finds its row of Q in the prefix table (same row as its neighbour almost always: one shared-memory
-//      probe), loads (c, q_jc) -- coalesced, a row of Q is contiguous -- and the extent of row c of H^T;
-//   3. contraction: the warp's 32 products are handed to sub-warp groups of G lanes (G ~ the mean row length of
-//      H^T), each lane walks its product's row of H^T with stride G.  Rows of H^T are sorted by DESCENDING k
-//      (transpose_impl), so the walk stops at the first k below the diagonal.  The first loads of four rounds
-//      are issued before any of them is used (memory-level parallelism instead of a serial per-thread walk).
-//   4. adds go to the shared window [w0, w1) (CAS loop on float64) or, beyond it, to C itself (L2 reduction);
+//   2. the products are taken 32 at a time by the warps, round-robin IN ORDER (chunk k goes to warp k mod nwarp):
+//      lane l of a warp takes product 32k + l, finds its row of Q in the prefix table, loads (c, q_jc) -- coalesced,
+//      a row of Q is contiguous, and streamed past L2 (evict-first: a row of Q is used once per row of C) -- and
+//      the extent of row c of H^T;
+//   3. contraction as ONE flat stream: the rows of H^T of the warp's 32 products are numbered by a warp prefix sum
+//      of their lengths and the warp walks the concatenation 32 entries per step.  The owner of an entry is found
+//      from a 32-bit mask of the row starts inside the step (one warp-wide OR reduction + popcount); its weight
+//      w = h_ij * q_jc and the offset of its row come from a 32-entry per-warp table in shared memory.  When
+//      consecutive products have consecutive c (banded Q) their rows of H^T are adjacent in memory, so every load
+//      of the stream is fully coalesced; for any other Q it is a balanced gather.  Every lane is active whatever
+//      the row lengths of H^T (the round-1 kernel walked one row per thread: 17.8 of 32 lanes active);
+//   4. entries with k >= i (upper mode) are added to the shared window [w0, w1) (float64 CAS loop) or, beyond it,
+//      to C itself (L2 reduction);
 //   5. the window is streamed out and cleared in one pass.
-// Dynamic shared memory: acc[win_cap] | hv[blockDim] (h_ij) | qs[blockDim] (first entry of row j of Q) |
-// pre[blockDim + 1] (exclusive prefix of the Q row lengths).
+//
+// SYNC (cooperative launch): the grid processes the rows in batches of gridDim.x, one row per block, with a grid
+// barrier between batches.  Rows of H are sorted by column and step 2 walks them in order, so all blocks sweep the
+// column range of H^T together: at any moment the chip reads a narrow band of H^T (cfg 5: ~20 MB of the 96 MB),
+// which stays L2 resident, instead of gathering from all of it (round 1: 36 GB of DRAM reads, L2 hit rate 50 %).
+// Without SYNC rows are handed out through an atomic ticket.
+//
+// Dynamic shared memory: acc[win_cap] | hv[nt] | w[nt] | qs[nt] | pre[nt + 1] | d[nt].
 struct TripleScratch {
     unsigned red[33];
     unsigned long long cnt[2];
     int row;
 };
 __host__ __device__ inline size_t triple_window_smem(int win_cap, int threads) {
-    return (size_t)win_cap * 8 + (size_t)threads * 16 + 16;
+    return (size_t)win_cap * 8 + (size_t)threads * 28 + 16;
 }
 
-template <bool UPPER, int G>
+__device__ __forceinline__ int ld_stream_i32(const int32_t* p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream_f64(const double* p) { return __ldcs(p); }
+
+// counters[3]: monotone arrival counter of the grid barrier (zeroed before the launch)
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1ULL);
+        while (*((volatile unsigned long long*)counter) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <bool UPPER, bool SYNC>
 __global__ void __launch_bounds__(1024, 1)
-k_triple_window(Csr H, Csr Q, Csr Ht, int ht_desc, int row_begin, int nrows, int win_cap,
+k_triple_window(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, int win_cap,
                 double* __restrict__ C, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ TripleScratch S;
     const int n = H.rows;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     double* acc = reinterpret_cast<double*>(s_raw);
     double* s_hv = acc + win_cap;                                   // win_cap is even: 16-byte aligned
-    int* s_qs = reinterpret_cast<int*>(s_hv + nt);
+    double* s_w = s_hv + nt + warp * 32;                            // this warp's 32 weights
+    int* s_qs = reinterpret_cast<int*>(s_hv + 2 * nt);
     unsigned* s_pre = reinterpret_cast<unsigned*>(s_qs + nt);
-    const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-    constexpr int NG = 32 / G;                 // groups per warp; a warp's 32 products take G rounds
-    constexpr int BATCH = G < 4 ? G : 4;       // rounds whose first loads are in flight together
-    const int grp = lane / G, sub = lane % G;
-    const bool desc = ht_desc != 0;
+    int* s_d = reinterpret_cast<int*>(s_pre + nt + 1) + warp * 32;  // this warp's 32 row offsets
+    const unsigned lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
     if (tid < 2) S.cnt[tid] = 0;
     for (int t = tid; t < win_cap; t += nt) acc[t] = 0.0;
     __syncthreads();
-    unsigned long long p1 = 0, p2 = 0;
-    while (true) {
-        if (tid == 0) S.row = (int)atomicAdd(counters + 2, 1ULL);
-        __syncthreads();
-        const int r = S.row;
-        __syncthreads();
-        if (r >= nrows) break;
-        const int i = row_begin + r;
-        const int lo = UPPER ? i : 0;
-        const int w0 = lo, w1 = min(n, lo + win_cap);
-        double* row = C + (size_t)r * n;
-        const int h_begin = __ldg(H.ptr + i), h_end = __ldg(H.ptr + i + 1);
-        // zeros left of the diagonal (never touched again: evict-first) and right of the window (about to take
-        // reductions: default policy so the lines stay in L2)
-        triple_stream_out(row, nullptr, w0);
-        for (int t = w1 + tid; t < n; t += nt) row[t] = 0.0;
-        for (int base = h_begin; base < h_end; base += nt) {
-            const int cnt = min(nt, h_end - base);
-            int qs = 0;
-            unsigned len = 0;
-            if (tid < cnt) {
-                const int j = __ldg(H.idx + base + tid);
-                qs = __ldg(Q.ptr + j);
-                len = (unsigned)(__ldg(Q.ptr + j + 1) - qs);
-                s_hv[tid] = __ldg(H.val + base + tid);
-                s_qs[tid] = qs;
-            }
-            unsigned total;
-            const unsigned ex = block_excl_scan<unsigned>(len, S.red, &total);
-            if (tid < cnt) s_pre[tid] = ex;
-            if (tid == 0) s_pre[cnt] = total;
-            __syncthreads();                               // tables complete; tail zeros ordered before reductions
-            if (tid == 0) p1 += total;
-            const unsigned wb = (unsigned)((unsigned long long)total * warp / nwarp);
-            const unsigned we = (unsigned)((unsigned long long)total * (warp + 1) / nwarp);
-            int r_base = 0;
-            if (wb < we) {                                 // row of the warp's first product (warp-uniform search)
-                int a = 0, b = cnt;
-                while (b - a > 1) {
-                    const int mid = (a + b) >> 1;
-                    if (s_pre[mid] <= wb) a = mid; else b = mid;
+    unsigned long long p1 = 0;
+    unsigned p2 = 0;
+    unsigned long long p2_total = 0;
+    const int nbatch = SYNC ? (nrows + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    for (int batch = 0; ; ++batch) {
+        int r;
+        if (SYNC) {
+            if (batch >= nbatch) break;
+            r = batch * (int)gridDim.x + (int)blockIdx.x;
+        } else {
+            if (tid == 0) S.row = (int)atomicAdd(counters + 2, 1ULL);
+            __syncthreads();
+            r = S.row;
+            __syncthreads();
+            if (r >= nrows) break;
+        }
+        if (r < nrows) {
+            const int i = row_begin + r;
+            const int lo = UPPER ? i : 0;
+            const int w0 = lo, w1 = min(n, lo + win_cap);
+            double* row = C + (size_t)r * n;
+            const int h_begin = __ldg(H.ptr + i), h_end = __ldg(H.ptr + i + 1);
+            // zeros left of the diagonal (never touched again: evict-first) and right of the window (about to take
+            // reductions: default policy so the lines stay in L2)
+            triple_stream_out(row, nullptr, w0);
+            for (int t = w1 + tid; t < n; t += nt) row[t] = 0.0;
+            for (int base = h_begin; base < h_end; base += nt) {
+                const int cnt = min(nt, h_end - base);
+                unsigned len = 0;
+                if (tid < cnt) {
+                    const int j = __ldg(H.idx + base + tid);
+                    const int qs = __ldg(Q.ptr + j);
+                    len = (unsigned)(__ldg(Q.ptr + j + 1) - qs);
+                    s_hv[tid] = __ldg(H.val + base + tid);
+                    s_qs[tid] = qs;
                 }
-                r_base = a;
-            }
-            for (unsigned f0 = wb; f0 < we; f0 += 32) {
-                const unsigned f = f0 + lane;
-                const bool valid = f < we;
-                int rr = r_base;
-                int hs = 0, he = 0;
-                double w = 0.0;
-                if (valid) {
-                    if (s_pre[rr + 1] <= f) {              // beyond the base row: largest rr with pre[rr] <= f
-                        int a = rr + 1, b = cnt;
+                unsigned total;
+                const unsigned ex = block_excl_scan<unsigned>(len, S.red, &total);
+                if (tid < cnt) s_pre[tid] = ex;
+                if (tid == 0) s_pre[cnt] = total;
+                __syncthreads();                           // tables complete; tail zeros ordered before reductions
+                if (tid == 0) p1 += total;
+                for (unsigned f0 = (unsigned)warp * 32u; f0 < total; f0 += (unsigned)nwarp * 32u) {
+                    const unsigned f = f0 + lane;
+                    const bool valid = f < total;
+                    int hs = 0;
+                    unsigned hlen = 0;
+                    double w = 0.0;
+                    if (valid) {
+                        int a = 0, b = cnt;                // largest a with pre[a] <= f  (pre[cnt] = total > f)
                         while (b - a > 1) {
                             const int mid = (a + b) >> 1;
                             if (s_pre[mid] <= f) a = mid; else b = mid;
                         }
-                        rr = a;
+                        const int q = s_qs[a] + (int)(f - s_pre[a]);
+                        const int c = ld_stream_i32(Q.idx + q);
+                        w = s_hv[a] * ld_stream_f64(Q.val + q);
+                        hs = __ldg(Ht.ptr + c);
+                        hlen = (unsigned)(__ldg(Ht.ptr + c + 1) - hs);
                     }
-                    const int q = s_qs[rr] + (int)(f - s_pre[rr]);
-                    const int c = __ldg(Q.idx + q);
-                    w = s_hv[rr] * __ldg(Q.val + q);
-                    hs = __ldg(Ht.ptr + c);
-                    he = __ldg(Ht.ptr + c + 1);
-                }
-                const unsigned last = min(31u, we - f0 - 1u);
-                r_base = __shfl_sync(FULL, rr, (int)last);
-                // contraction of the warp's 32 products, G lanes per product
-#pragma unroll 1
-                for (int rd = 0; rd < G; rd += BATCH) {
-                    int q[BATCH], pe[BATCH], k[BATCH];
-                    double pw[BATCH], v[BATCH];
-#pragma unroll
-                    for (int b = 0; b < BATCH; ++b) {
-                        const int p = (rd + b) * NG + grp;
-                        q[b] = __shfl_sync(FULL, hs, p) + sub;
-                        pe[b] = __shfl_sync(FULL, he, p);
-                        pw[b] = __shfl_sync(FULL, w, p);
-                        k[b] = q[b] < pe[b] ? __ldg(Ht.idx + q[b]) : -1;
+                    // flat numbering of the entries of the 32 rows of H^T
+                    const unsigned incl = warp_incl_scan(hlen);
+                    const unsigned pre = incl - hlen;
+                    const unsigned L = __shfl_sync(FULL, incl, 31);
+                    const unsigned nonempty = __ballot_sync(FULL, hlen > 0);
+                    if (hlen > 0) {
+                        const int rank = __popc(nonempty & lt_mask);
+                        s_w[rank] = w;
+                        s_d[rank] = hs - (int)pre;
                     }
-#pragma unroll
-                    for (int b = 0; b < BATCH; ++b) v[b] = k[b] >= lo ? __ldg(Ht.val + q[b]) : 0.0;
-#pragma unroll
-                    for (int b = 0; b < BATCH; ++b) {
-                        if (k[b] >= lo) {
-                            const double x = pw[b] * v[b];
-                            if (k[b] < w1) atomicAdd(acc + (k[b] - w0), x); else atomicAdd(row + k[b], x);
-                            ++p2;
-                        }
-                        // rest of a row of H^T longer than G (descending rows: a cut lane has nothing further)
-                        if (k[b] >= lo || (!desc && k[b] >= 0)) {
-                            for (int qq = q[b] + G; qq < pe[b]; qq += G) {
-                                const int kk = __ldg(Ht.idx + qq);
-                                if (kk < lo) { if (desc) break; else continue; }
-                                const double x = pw[b] * __ldg(Ht.val + qq);
-                                if (kk < w1) atomicAdd(acc + (kk - w0), x); else atomicAdd(row + kk, x);
+                    __syncwarp();
+                    int heads_before = 0;
+                    for (unsigned eb = 0; eb < L; eb += 32) {
+                        const unsigned bit = (hlen > 0 && pre >= eb && pre < eb + 32) ? 1u << (pre - eb) : 0u;
+                        const unsigned heads = __reduce_or_sync(FULL, bit);
+                        const int owner = heads_before + __popc(heads & le_mask) - 1;
+                        heads_before += __popc(heads);
+                        const unsigned p = eb + lane;
+                        if (p < L) {
+                            const int addr = (int)p + s_d[owner];
+                            const int k = __ldg(Ht.idx + addr);
+                            if (k >= lo) {
+                                const double x = s_w[owner] * __ldg(Ht.val + addr);
+                                if (k < w1) atomicAdd(acc + (k - w0), x); else atomicAdd(row + k, x);
                                 ++p2;
                             }
                         }
                     }
+                    __syncwarp();                          // the per-warp tables are rewritten by the next chunk
                 }
+                __syncthreads();                           // tables are rewritten by the next slice / row
             }
-            __syncthreads();                               // tables are rewritten by the next slice / row
-        }
-        // window out (coalesced 128-bit streaming stores) and cleared for the next row
-        {
+            p2_total += p2;
+            p2 = 0;
+            // window out (coalesced 128-bit streaming stores) and cleared for the next row
             const int count = w1 - w0;
             double* dst = row + w0;
             const int head = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1);
@@ -225,9 +238,10 @@ k_triple_window(Csr H, Csr Q, Csr Ht, int ht_desc, int row_begin, int nrows, int
             const int tail = head + 2 * pairs;
             if (tail < count && tid == nt - 1) { st_stream_f64(dst + tail, acc[tail]); acc[tail] = 0.0; }
         }
-        // (the ticket barrier at the top of the loop orders the clearing before the next row's adds)
+        if (SYNC) grid_barrier(counters + 3, (unsigned long long)(batch + 1) * gridDim.x);
+        else __syncthreads();                              // clearing ordered before the next row's adds
     }
-    triple_flush_counters(p1, p2, S.cnt, counters);
+    triple_flush_counters(p1, p2_total, S.cnt, counters);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -275,9 +289,9 @@ k_triple_rows_red(Csr H, Csr Q, Csr Ht, int ht_desc, int row_begin, int nrows,
 // ---------------------------------------------------------------------------------------------------
 static size_t g_triple_smem_optin = 0, g_triple_smem_sm = 0;
 
-template <bool UPPER, int G>
+template <bool UPPER, bool SYNC>
 static cudaError_t configure_window() {
-    return cudaFuncSetAttribute(k_triple_window<UPPER, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(k_triple_window<UPPER, SYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(g_triple_smem_optin - sizeof(TripleScratch) - 64));
 }
 
@@ -291,12 +305,10 @@ cudaError_t triple_kernels_configure() {
     if (e != cudaSuccess) return e;
     g_triple_smem_optin = (size_t)optin;
     g_triple_smem_sm = (size_t)per_sm;
-    if ((e = configure_window<true, 4>()) != cudaSuccess) return e;
-    if ((e = configure_window<true, 8>()) != cudaSuccess) return e;
-    if ((e = configure_window<true, 32>()) != cudaSuccess) return e;
-    if ((e = configure_window<false, 4>()) != cudaSuccess) return e;
-    if ((e = configure_window<false, 8>()) != cudaSuccess) return e;
-    return configure_window<false, 32>();
+    if ((e = configure_window<true, true>()) != cudaSuccess) return e;
+    if ((e = configure_window<true, false>()) != cudaSuccess) return e;
+    if ((e = configure_window<false, true>()) != cudaSuccess) return e;
+    return configure_window<false, false>();
 }
 
 static int env_int(const char* name, int dflt) {
@@ -304,16 +316,15 @@ static int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-template <bool UPPER>
-static void launch_window(int group, int grid, int threads, size_t smem, cudaStream_t st, const Csr& H, const Csr& Q,
-                          const Csr& Ht, int ht_desc, int row_begin, int nrows, int win_cap, double* d_c,
-                          unsigned long long* d_counters) {
-    if (group <= 4)
-        k_triple_window<UPPER, 4><<<grid, threads, smem, st>>>(H, Q, Ht, ht_desc, row_begin, nrows, win_cap, d_c, d_counters);
-    else if (group <= 8)
-        k_triple_window<UPPER, 8><<<grid, threads, smem, st>>>(H, Q, Ht, ht_desc, row_begin, nrows, win_cap, d_c, d_counters);
-    else
-        k_triple_window<UPPER, 32><<<grid, threads, smem, st>>>(H, Q, Ht, ht_desc, row_begin, nrows, win_cap, d_c, d_counters);
+template <bool UPPER, bool SYNC>
+static cudaError_t launch_window(int grid, int threads, size_t smem, cudaStream_t st, Csr H, Csr Q, Csr Ht, int row_begin,
+                                 int nrows, int win_cap, double* d_c, unsigned long long* d_counters) {
+    if (!SYNC) {
+        k_triple_window<UPPER, false><<<grid, threads, smem, st>>>(H, Q, Ht, row_begin, nrows, win_cap, d_c, d_counters);
+        return cudaGetLastError();
+    }
+    void* args[] = {&H, &Q, &Ht, &row_begin, &nrows, &win_cap, &d_c, &d_counters};
+    return cudaLaunchCooperativeKernel((const void*)k_triple_window<UPPER, true>, dim3(grid), dim3(threads), args, smem, st);
 }
 
 cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool ht_desc,
@@ -363,15 +374,21 @@ cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const
     const int threads = 1024 / per_sm;
     int grid = lc.sm_count * per_sm;
     if (grid > nrows) grid = nrows;
-    // lanes per row of H^T ~ its mean length (upper mode keeps about half of each row on average)
-    const double mean_len = Ht.rows > 0 ? (double)ht_nnz / (double)Ht.rows : 1.0;
-    int group = mean_len <= 10.0 ? 4 : mean_len <= 24.0 ? 8 : 32;
-    group = env_int("SPGEMM_B200_TRIPLE_GROUP", group);
     const size_t smem = triple_window_smem(win, threads);
-    const int d = ht_desc ? 1 : 0;
-    if (upper_only) launch_window<true>(group, grid, threads, smem, lc.stream, H, Q, Ht, d, row_begin, nrows, win, d_c, d_counters);
-    else launch_window<false>(group, grid, threads, smem, lc.stream, H, Q, Ht, d, row_begin, nrows, win, d_c, d_counters);
-    SB_LAUNCH_CHECK(lc);
+    // lock-step batches (grid barrier) pay when H^T is too big to stay in L2 whatever the order of the gathers
+    const double ht_bytes = 12.0 * (double)ht_nnz + 4.0 * (double)Ht.rows;
+    const bool sync = env_int("SPGEMM_B200_TRIPLE_SYNC", ht_bytes > 40.0e6 ? 1 : 0) != 0 && grid > 1;
+    cudaError_t e = cudaErrorUnknown;
+    if (sync) {
+        e = upper_only ? launch_window<true, true>(grid, threads, smem, lc.stream, H, Q, Ht, row_begin, nrows, win, d_c, d_counters)
+                       : launch_window<false, true>(grid, threads, smem, lc.stream, H, Q, Ht, row_begin, nrows, win, d_c, d_counters);
+        if (e != cudaSuccess) cudaGetLastError();          // not co-resident (another kernel holds SMs): ticket mode
+    }
+    if (e != cudaSuccess)
+        e = upper_only ? launch_window<true, false>(grid, threads, smem, lc.stream, H, Q, Ht, row_begin, nrows, win, d_c, d_counters)
+                       : launch_window<false, false>(grid, threads, smem, lc.stream, H, Q, Ht, row_begin, nrows, win, d_c, d_counters);
+    if (e != cudaSuccess) return e;
+    ++*lc.launches;
     return cudaSuccess;
 }
 
