@@ -216,11 +216,14 @@ def cpu_sample(w, name, threads, max_seconds=25.0):
         return (lambda: port.spgemm_dense(a, b, sym)), flops, "port", 1, f"full {name}: oracle port, 1 thread"
     if kind == "sparse":
         sym = bool(w["kwargs"].get("symmetric"))
-        # the only working reference build of the sparse-output path is the shipped serial binary
+        # today's src/ cannot run its sparse-output path.  Preferred: the same sources with the
+        # Appendix-B repairs (oracle/build_patched_ref.py), multi-threaded and bit-identical to the shipped binary;
+        # else the shipped serial binary; else the oracle port.
+        patched = have_ref and ref.patched_available()
         p_rows = np.add.reduceat(np.diff(b.indptr).astype(np.int64)[a.indices], a.indptr[:-1][np.diff(a.indptr) > 0]) \
             if a.nnz else np.zeros(0)
         total = int(p_rows.sum())
-        budget = int(2.0e7 * max_seconds)              # ~20 M products/s serial
+        budget = int(2.0e7 * max_seconds * (max(1, cores // 2) if patched else 1))    # ~20 M products/s per core
         if total <= budget:
             sub, desc = a, f"full {name}"
         else:
@@ -229,6 +232,10 @@ def cpu_sample(w, name, threads, max_seconds=25.0):
             rows = int(np.searchsorted(np.cumsum(per_row), budget)) + 1
             sub, desc = a[:rows], f"rows [0,{rows}) of {name} ({budget / total:.1%} of the products)"
         flops = 2 * count_products(sub, b)
+        if patched:
+            return (lambda: ref.omp_patched().sparse(sub, b, sym, copy=False)), flops, "reference", cores, \
+                desc + ": reference sparse_" + ("sym" if sym else "nosym") + " from src/ with the SURVEY Appendix-B " \
+                "repairs (-O3 -fopenmp; bit-identical to the shipped binary), C call only"
         if have_ref:
             return (lambda: ref.shipped().sparse(sub, b, sym, copy=False)), flops, "reference", 1, \
                 desc + ": reference shipped libsparse_x86_64.so sparse_nosym (serial build, 1 thread)"
@@ -630,19 +637,17 @@ def run_ours(args, w, name, info, flops, rank, world, threads):
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": cflops / dt / 1e9, "unit": UNIT, "cores": cores, "kind": ckind,
                                 "sample": desc, "seconds": dt, "first_call_seconds": first}
-        if kind == "sparse":
-            # the reference has no working multi-threaded sparse path; for scale, the oracle's
-            # OpenMP port of it (bit-identical rows, dynamic row blocks) on every host core
-            from oracle import port
+        if kind == "sparse" and ckind == "reference" and cores > 1:
+            # beside it: the reference's shipped (serial) binary on the same sample
+            from oracle import ref
             sym = bool(w["kwargs"].get("symmetric"))
             sub = a if "full" in desc else a[:int(desc.split("[0,")[1].split(")")[0])]
-            port.spgemm_csr(sub, b, sym, omp_blocks=16 * threads, copy=False)          # warm-up (threads, pages)
             t0 = time.perf_counter()
-            port.spgemm_csr(sub, b, sym, omp_blocks=16 * threads, copy=False)
+            ref.shipped().sparse(sub, b, sym, copy=False)
             dt = time.perf_counter() - t0
-            line["cpu_baseline_omp_port"] = {"value": cflops / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-                                             "sample": desc.split(":")[0] + ": oracle_spgemm_csr_omp, C call only",
-                                             "seconds": dt}
+            line["cpu_baseline_shipped_serial"] = {"value": cflops / dt / 1e9, "unit": UNIT, "cores": 1,
+                                                   "kind": "reference", "seconds": dt,
+                                                   "sample": desc.split(":")[0] + ": shipped libsparse_x86_64.so, 1 thread"}
     if world == 1 and name == DEFAULT_WORKLOAD and not args.no_per_config:
         del w, a, b
         gc.collect()

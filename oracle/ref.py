@@ -10,6 +10,11 @@ prebuilt files):
                             (include/matrix_def.h:17-31).  dense_nosym / dense_sym / triple_product work
                             and are bit-identical to the shipped binary; sparse_* are defective.
 
+  libsparse_ref_omp_patched.so  the same sources with the repairs of SURVEY.md Appendix B applied in memory at
+                            build time (oracle/build_patched_ref.py): the reference's multi-threaded sparse_nosym /
+                            sparse_sym with a working body -- bit-identical to the shipped binary
+                            (tests/test_oracle.py), used as the many-core CPU baseline of the sparse-output path.
+
 Raw C calls only (no reference Python on the path) so that timing measures the C routine itself.
 """
 import ctypes
@@ -117,6 +122,17 @@ def shipped():
     if "shipped" not in _cache:
         _cache["shipped"] = RefLib("libsparse_ref_shipped.so", size_t_fields=False)
     return _cache["shipped"]
+
+
+def patched_available():
+    return os.path.exists(os.path.join(_DIR, "libsparse_ref_omp_patched.so"))
+
+
+def omp_patched():
+    """Appendix-B-repaired OpenMP build: every mode usable, multi-threaded."""
+    if "patched" not in _cache:
+        _cache["patched"] = RefLib("libsparse_ref_omp_patched.so", size_t_fields=True)
+    return _cache["patched"]
 
 
 def omp():

@@ -1,5 +1,8 @@
 // analysis.cu -- the passes that replace the reference's row partitioner (src/workdivision.cpp:16-89):
 // per-row intermediate-product counts, cost binning, scans, CSR transpose, sortedness check.
+#include <cstdio>
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace sb {
@@ -86,13 +89,29 @@ cudaError_t launch_row_products(const LaunchCtx& lc, const Csr& A, const Csr& B,
 __global__ void __launch_bounds__(256)
 k_check_csr(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, int rows, int cols, int64_t nnz,
             int32_t* __restrict__ flags) {
+    // entries: four per thread (one 128-bit load when aligned) plus the first entry of the next quad
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t q0 = t * 4;
     int any = 0, edge = 0, bad = 0;
-    if (t < nnz) {
-        const int c = __ldg(idx + t);
-        bad = c < 0 || c >= cols;
-        if (t + 1 < nnz) any = c > __ldg(idx + t + 1);
+    if (q0 < nnz) {
+        int c[5];
+        if (q0 + 4 <= nnz && (reinterpret_cast<uintptr_t>(idx) & 15) == 0) {
+            const int4 v = __ldg(reinterpret_cast<const int4*>(idx) + t);
+            c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c[u] = q0 + u < nnz ? __ldg(idx + q0 + u) : 0x7fffffff;
+        }
+        c[4] = q0 + 4 < nnz ? __ldg(idx + q0 + 4) : 0x7fffffff;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (q0 + u < nnz) {
+                bad |= c[u] < 0 || c[u] >= cols;
+                if (q0 + u + 1 < nnz) any += c[u] > c[u + 1];
+            }
+        }
     }
+    // rows: one per thread
     if (t < rows) {
         const int s = __ldg(ptr + t), e = __ldg(ptr + t + 1);
         if (s < 0 || e < s || (int64_t)e > nnz) bad = 1;
@@ -100,9 +119,10 @@ k_check_csr(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, in
         if (t == 0 && s != 0) bad = 1;
         if (t == rows - 1 && (int64_t)e != nnz) bad = 1;
     }
-    const unsigned m_any = __ballot_sync(FULL, any), m_edge = __ballot_sync(FULL, edge), m_bad = __ballot_sync(FULL, bad);
+    any = warp_sum(any);
+    const unsigned m_edge = __ballot_sync(FULL, edge), m_bad = __ballot_sync(FULL, bad);
     if (lane_id() == 0) {
-        if (m_any) atomicAdd(flags + 1, __popc(m_any));
+        if (any) atomicAdd(flags + 1, any);
         if (m_edge) atomicAdd(flags + 2, __popc(m_edge));
         if (m_bad) atomicAdd(flags + 3, __popc(m_bad));
     }
@@ -114,7 +134,8 @@ __global__ void k_sorted_flag(int32_t* __restrict__ flags) {
 cudaError_t launch_check_csr(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_flags) {
     cudaError_t e = cudaMemsetAsync(d_flags, 0, 4 * sizeof(int32_t), lc.stream);
     if (e != cudaSuccess) return e;
-    const int64_t n = nnz > X.rows ? nnz : X.rows;
+    const int64_t quads = (nnz + 3) / 4;
+    const int64_t n = quads > X.rows ? quads : X.rows;
     if (n > 0) {
         const int threads = 256;
         const int64_t blocks = (n + threads - 1) / threads;
@@ -262,18 +283,31 @@ k_transpose_count(const int32_t* __restrict__ idx, int64_t nnz, int32_t* __restr
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nnz) atomicAdd(counts + __ldg(idx + t), 1);
 }
+// LANES lanes per row of X (8 for short rows, 32 for rows of ~100+ entries); two entries per lane in flight
+template <int LANES>
 __global__ void __launch_bounds__(256)
 k_transpose_fill(Csr X, const int32_t* __restrict__ t_ptr, int32_t* __restrict__ cursor, int32_t* __restrict__ t_idx,
                  double* __restrict__ t_val) {
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const int gl = threadIdx.x & 7;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const int gl = threadIdx.x % LANES;
     if (r >= X.rows) return;
     const int s = __ldg(X.ptr + r), e = __ldg(X.ptr + r + 1);
-    for (int p = s + gl; p < e; p += 8) {
-        const int c = __ldg(X.idx + p);
-        const int pos = __ldg(t_ptr + c) + atomicAdd(cursor + c, 1);
-        t_idx[pos] = r;
-        t_val[pos] = __ldg(X.val + p);
+    for (int p = s + gl; p < e; p += 2 * LANES) {
+        const int p2 = p + LANES;
+        const int c0 = __ldg(X.idx + p);
+        const int c1 = p2 < e ? __ldg(X.idx + p2) : -1;
+        const double v0 = __ldg(X.val + p);
+        const double v1 = p2 < e ? __ldg(X.val + p2) : 0.0;
+        const int b0 = __ldg(t_ptr + c0);
+        const int b1 = c1 >= 0 ? __ldg(t_ptr + c1) : 0;
+        const int o0 = atomicAdd(cursor + c0, 1);
+        const int o1 = c1 >= 0 ? atomicAdd(cursor + c1, 1) : 0;
+        t_idx[b0 + o0] = r;
+        t_val[b0 + o0] = v0;
+        if (c1 >= 0) {
+            t_idx[b1 + o1] = r;
+            t_val[b1 + o1] = v1;
+        }
     }
 }
 cudaError_t launch_transpose_count(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_counts) {
@@ -282,11 +316,13 @@ cudaError_t launch_transpose_count(const LaunchCtx& lc, const Csr& X, int64_t nn
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
 }
-cudaError_t launch_transpose_fill(const LaunchCtx& lc, const Csr& X, const int32_t* t_ptr, int32_t* d_cursor,
-                                  int32_t* t_idx, double* t_val) {
+cudaError_t launch_transpose_fill(const LaunchCtx& lc, const Csr& X, int64_t nnz, const int32_t* t_ptr,
+                                  int32_t* d_cursor, int32_t* t_idx, double* t_val) {
     if (X.rows <= 0) return cudaSuccess;
-    const int blocks = (X.rows + 31) / 32;
-    k_transpose_fill<<<blocks, 256, 0, lc.stream>>>(X, t_ptr, d_cursor, t_idx, t_val);
+    if (nnz >= (int64_t)48 * X.rows)
+        k_transpose_fill<32><<<(X.rows + 7) / 8, 256, 0, lc.stream>>>(X, t_ptr, d_cursor, t_idx, t_val);
+    else
+        k_transpose_fill<8><<<(X.rows + 31) / 32, 256, 0, lc.stream>>>(X, t_ptr, d_cursor, t_idx, t_val);
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
 }
@@ -393,14 +429,14 @@ cudaError_t launch_narrow_indptr(const LaunchCtx& lc, const int64_t* in, int32_t
 // ---------------------------------------------------------------------------------------------------
 // Cost of row i of the triple product H Q H^T for the flop-balanced multi-GPU split:
 //   P1_i = sum over (i,j) in H of nnz(Q[j,:])                         (expansion of H[i,:] Q)
-//   P2_i = sum over those (j,c) of nnz(H^T[c,:])                      (contraction against H^T), scaled by the
-//          fraction (n - i) / n of columns kept when only the upper triangle is computed.
-// cost_i = 7 * P1_i + P2_i: every product of the expansion pays its gathers of Q and of the extent of its row of H^T
-// whether or not any entry survives the k >= i cut; fitted to the per-rank kernel times of cfg 5 on four B200s
-// (t(x) ~ 15.4 + 17.3 (1 - x) per unit of rows at relative position x, i.e. one product ~ 7 visited entries).
-// One warp per row.
+//   P2_i = sum over those (j,c) of nnz(H^T[c,:])                      (entries of H^T the contraction streams)
+// cost_i = a * P1_i + b * P2_i + c * P2_i * (n - i) / n: every product pays its gathers of Q and of the extent of
+// its row of H^T (a), every entry of that row is read and tested against the diagonal (b), and the fraction
+// (n - i) / n that survives the k >= i cut of the upper-triangle mode is multiplied and accumulated (c).
+// (a, b, c) are fitted to the per-rank kernel times of cfg 5 (profiles/r2); SPGEMM_B200_TRIPLE_COST="a,b,c"
+// overrides them.  One warp per row.
 __global__ void __launch_bounds__(256)
-k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, int64_t* __restrict__ costs) {
+k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, double ca, double cb, double cc, int64_t* __restrict__ costs) {
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= H.rows) return;
     long long p1 = 0, p2 = 0;
@@ -412,14 +448,16 @@ k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, int64_t* __restrict__ costs
     p1 = warp_sum(p1);
     p2 = warp_sum(p2);
     if (lane_id() == 0) {
-        if (upper_only) p2 = (long long)((double)p2 * (double)(H.rows - row) / (double)H.rows);
-        costs[row] = 7 * p1 + p2;
+        const double keep = upper_only ? (double)(H.rows - row) / (double)H.rows : 1.0;
+        costs[row] = (long long)(ca * (double)p1 + cb * (double)p2 + cc * (double)p2 * keep);
     }
 }
 cudaError_t launch_triple_costs(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool upper_only,
                                 int64_t* d_costs) {
     if (H.rows <= 0) return cudaSuccess;
-    k_triple_costs<<<(H.rows + 7) / 8, 256, 0, lc.stream>>>(H, Q, Ht, upper_only ? 1 : 0, d_costs);
+    double ca = 4.0, cb = 1.0, cc = 2.0;
+    if (const char* v = getenv("SPGEMM_B200_TRIPLE_COST")) sscanf(v, "%lf,%lf,%lf", &ca, &cb, &cc);
+    k_triple_costs<<<(H.rows + 7) / 8, 256, 0, lc.stream>>>(H, Q, Ht, upper_only ? 1 : 0, ca, cb, cc, d_costs);
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
 }

@@ -374,8 +374,9 @@ void result_release(spgemm_b200_result* r) {
     delete r;
 }
 
-// Build X^T on the device with every row sorted by DESCENDING column (see launch_sort_rows).
-int transpose_impl(const spgemm_b200_mat* x, spgemm_b200_mat** out) {
+// Build X^T on the device; sort_desc: every row sorted by DESCENDING column (see launch_sort_rows), else rows come
+// out in the arrival order of the scatter (all the window kernel of the triple product needs).
+int transpose_impl(const spgemm_b200_mat* x, spgemm_b200_mat** out, bool sort_desc) {
     Ctx& g = cx();
     NvtxRange nv("spgemm_b200:transpose");
     spgemm_b200_mat* t = new spgemm_b200_mat{x->cols, x->rows, x->nnz, nullptr, nullptr, nullptr, true, g.device,
@@ -394,11 +395,11 @@ int transpose_impl(const spgemm_b200_mat* x, spgemm_b200_mat** out) {
     if (e == cudaSuccess) e = cudaMemsetAsync(cursor, 0, ((size_t)t->rows + 1) * 4, g.stream);
     if (e == cudaSuccess) e = launch_transpose_count(lc, view(x), x->nnz, counts);
     if (e == cudaSuccess) e = launch_scan_i32(lc, counts, t->ptr, t->rows, tmp);
-    if (e == cudaSuccess) e = launch_transpose_fill(lc, view(x), t->ptr, cursor, t->idx, t->val);
+    if (e == cudaSuccess) e = launch_transpose_fill(lc, view(x), x->nnz, t->ptr, cursor, t->idx, t->val);
     // rows of the transpose come out in atomic order: sort them by descending column (counts is reused as the
     // list of rows too long for the per-thread sort)
-    if (e == cudaSuccess) e = launch_sort_rows(lc, t->rows, t->ptr, t->idx, t->val, counts, true);
-    t->desc_sorted = true;
+    if (e == cudaSuccess && sort_desc) e = launch_sort_rows(lc, t->rows, t->ptr, t->idx, t->val, counts, true);
+    t->desc_sorted = sort_desc;
     dfree(counts); dfree(cursor); dfree(tmp);
     if (e != cudaSuccess) {
         mat_release(t);
@@ -826,7 +827,7 @@ int spgemm_b200_mat_transpose(const spgemm_b200_mat* x, spgemm_b200_mat** out) {
     ENTER_DEVICE(x->device);
     int rc = ensure_checked(const_cast<spgemm_b200_mat*>(x));
     if (rc) return rc;
-    return transpose_impl(x, out);
+    return transpose_impl(x, out, true);
 }
 
 int spgemm_b200_mat_sort(spgemm_b200_mat* x) {
@@ -1041,7 +1042,7 @@ int spgemm_b200_triple_dev(const spgemm_b200_mat* h, const spgemm_b200_mat* q, c
     if (ht && (rc = ensure_checked(const_cast<spgemm_b200_mat*>(ht)))) return rc;
     spgemm_b200_mat* own_ht = nullptr;
     if (!ht) {
-        if ((rc = transpose_impl(h, &own_ht))) return rc;
+        if ((rc = transpose_impl(h, &own_ht, env_mode("SPGEMM_B200_TRIPLE_MODE") == 2))) return rc;
         ht = own_ht;
     }
     mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
@@ -1088,7 +1089,7 @@ int spgemm_b200_triple(int n, int k, const int32_t* h_indptr, const int32_t* h_i
         mark(EV_H2D);
     }
     if ((rc = ensure_checked(h, q))) return done(rc);
-    if ((rc = transpose_impl(h, &ht))) return done(rc);
+    if ((rc = transpose_impl(h, &ht, env_mode("SPGEMM_B200_TRIPLE_MODE") == 2))) return done(rc);
     mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
     const size_t elems = (size_t)n * (size_t)n;
     if ((rc = dalloc(&d_c, elems)) || (rc = dalloc(&d_cnt, 4))) return done(rc);

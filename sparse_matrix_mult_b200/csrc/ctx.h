@@ -117,7 +117,7 @@ void finish_stats();
 int upload(int rows, int cols, const int32_t* ptr, const int32_t* idx, const double* val, spgemm_b200_mat** out);
 void mat_release(spgemm_b200_mat* m);             // frees device arrays on cx() and deletes the handle
 void result_release(spgemm_b200_result* r);
-int transpose_impl(const spgemm_b200_mat* x, spgemm_b200_mat** out);
+int transpose_impl(const spgemm_b200_mat* x, spgemm_b200_mat** out, bool sort_desc);
 // validation + sortedness of up to two matrices with ONE host synchronisation; ERR_ARG when an index is out of
 // range or an indptr is not monotone
 int ensure_checked(spgemm_b200_mat* m1, spgemm_b200_mat* m2 = nullptr);

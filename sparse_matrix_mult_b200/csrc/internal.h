@@ -54,8 +54,8 @@ cudaError_t launch_bin_by_nnz(const LaunchCtx& lc, const int32_t* d_nnz, int nro
 
 // CSR transpose: counts -> scan -> fill.  Rows of the transpose come out in arbitrary order.
 cudaError_t launch_transpose_count(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_counts);
-cudaError_t launch_transpose_fill(const LaunchCtx& lc, const Csr& X, const int32_t* t_ptr, int32_t* d_cursor,
-                                  int32_t* t_idx, double* t_val);
+cudaError_t launch_transpose_fill(const LaunchCtx& lc, const Csr& X, int64_t nnz, const int32_t* t_ptr,
+                                  int32_t* d_cursor, int32_t* t_idx, double* t_val);
 
 // rows sorted by column (ascending or descending), in place, any row length; d_long_list: int32[rows + 1] scratch
 cudaError_t launch_sort_rows(const LaunchCtx& lc, int rows, const int32_t* ptr, int32_t* idx, double* val,

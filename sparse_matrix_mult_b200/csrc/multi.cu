@@ -117,7 +117,7 @@ void worker(Job* job, int d) {
         mark(EV_H2D);
     }
     if (!rc) rc = ensure_checked(a, b);
-    if (!rc && job->kind == K_TRIPLE) rc = transpose_impl(a, &ht);
+    if (!rc && job->kind == K_TRIPLE) rc = transpose_impl(a, &ht, false);
     if (!rc && d == 0) {
         std::vector<int64_t> costs((size_t)m);
         rc = dalloc(&d_costs, (size_t)m);

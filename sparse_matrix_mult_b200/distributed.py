@@ -39,7 +39,8 @@ def partition_by_cost(costs, parts):
 
 def host_row_costs(a, b, kind, upper_only):
     """Per-row cost on the host (numpy): products of A rows against B; for the triple product
-    7 P1_i + P2_i * (n - i)/n, the same model as k_triple_costs (csrc/analysis.cu)."""
+    a P1_i + b P2_i + c P2_i (n - i)/n with (a, b, c) = (4, 1, 2), the same model as k_triple_costs
+    (csrc/analysis.cu)."""
     blen = np.diff(b.indptr).astype(np.int64)
     rows = np.repeat(np.arange(a.shape[0]), np.diff(a.indptr))
     p1 = np.bincount(rows, weights=blen[a.indices], minlength=a.shape[0]).astype(np.float64)
@@ -52,10 +53,11 @@ def host_row_costs(a, b, kind, upper_only):
     cum = np.concatenate([[0], np.cumsum(ht_len[b.indices])])
     qcost = (cum[b.indptr[1:]] - cum[b.indptr[:-1]]).astype(np.float64)
     p2 = np.bincount(rows, weights=qcost[a.indices], minlength=a.shape[0])
+    keep = 1.0
     if upper_only:
         n = a.shape[0]
-        p2 = p2 * (n - np.arange(n)) / max(1, n)
-    return 7.0 * p1 + p2
+        keep = (n - np.arange(n)) / max(1, n)
+    return 4.0 * p1 + 1.0 * p2 + 2.0 * p2 * keep
 
 
 # ------------------------------------------------------------------------------------------------------

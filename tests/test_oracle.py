@@ -104,3 +104,20 @@ def test_openmp_port_is_bit_identical_to_the_serial_port():
     y = sp.random(53, 41, density=0.2, format='csr', random_state=rng)
     got, want = port.spgemm_csr(x, y, omp_blocks=8), port.spgemm_csr(x, y)
     assert np.array_equal(got.indices, want.indices) and np.array_equal(got.data, want.data)
+
+
+def test_patched_openmp_reference_is_bit_identical_to_the_shipped_binary():
+    """today's src/ with the six repairs applied at build time (oracle/build_patched_ref.py)
+    reproduces the shipped serial binary bit for bit -- structure in first-touch order and values -- at any thread
+    count, on cfg 1 and on R-MAT scale 12 (power-law rows), both sparse modes."""
+    from oracle import ref
+    if not (ref.available() and ref.patched_available()):
+        pytest.skip("oracle/_ref not built (make -C oracle ref)")
+    from sparse_matrix_mult_b200 import synthetic
+    for name in ("cfg1", "cfg4r12"):
+        w = synthetic.workload(name)
+        for sym in (False, True):
+            a = ref.shipped().sparse(w["a"], w["b"], sym)
+            b = ref.omp_patched().sparse(w["a"], w["b"], sym)
+            assert a.nnz == b.nnz and np.array_equal(a.indptr, b.indptr), (name, sym)
+            assert np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data), (name, sym)
