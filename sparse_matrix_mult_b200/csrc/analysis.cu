@@ -310,6 +310,75 @@ k_transpose_fill(Csr X, const int32_t* __restrict__ t_ptr, int32_t* __restrict__
         }
     }
 }
+// ---------------------------------------------------------------------------------------------------
+// Paneled transpose (triple product): rows [row_begin, row_end) of X are cut into panels of `panel_w` rows and the
+// transposes of the panels are stored back to back as ONE CSR with np * X.cols rows -- row p * X.cols + c holds the
+// entries (r, x_rc) of column c with r in panel p.  t_ptr + p * X.cols is then the row-pointer array of panel p's
+// transpose over the shared idx / val arrays.  The triple product accumulates one column panel of C at a time, so
+// the slice of H^T it gathers from (a few tens of MB) stays L2 resident.
+template <int LANES>
+__global__ void __launch_bounds__(256)
+k_transpose_count_panels(Csr X, int row_begin, int row_end, int panel_w, int32_t* __restrict__ counts) {
+    const int r = row_begin + (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const int gl = threadIdx.x % LANES;
+    if (r >= row_end) return;
+    int32_t* base = counts + (size_t)((r - row_begin) / panel_w) * X.cols;
+    const int s = __ldg(X.ptr + r), e = __ldg(X.ptr + r + 1);
+    for (int p = s + gl; p < e; p += LANES) atomicAdd(base + __ldg(X.idx + p), 1);
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(256)
+k_transpose_fill_panels(Csr X, int row_begin, int row_end, int panel_w, const int32_t* __restrict__ t_ptr,
+                        int32_t* __restrict__ cursor, int32_t* __restrict__ t_idx, double* __restrict__ t_val) {
+    const int r = row_begin + (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const int gl = threadIdx.x % LANES;
+    if (r >= row_end) return;
+    const size_t off = (size_t)((r - row_begin) / panel_w) * X.cols;
+    const int s = __ldg(X.ptr + r), e = __ldg(X.ptr + r + 1);
+    for (int p = s + gl; p < e; p += 2 * LANES) {
+        const int p2 = p + LANES;
+        const int c0 = __ldg(X.idx + p);
+        const int c1 = p2 < e ? __ldg(X.idx + p2) : -1;
+        const double v0 = __ldg(X.val + p);
+        const double v1 = p2 < e ? __ldg(X.val + p2) : 0.0;
+        const int b0 = __ldg(t_ptr + off + c0);
+        const int b1 = c1 >= 0 ? __ldg(t_ptr + off + c1) : 0;
+        const int o0 = atomicAdd(cursor + off + c0, 1);
+        const int o1 = c1 >= 0 ? atomicAdd(cursor + off + c1, 1) : 0;
+        t_idx[b0 + o0] = r;
+        t_val[b0 + o0] = v0;
+        if (c1 >= 0) {
+            t_idx[b1 + o1] = r;
+            t_val[b1 + o1] = v1;
+        }
+    }
+}
+
+cudaError_t launch_transpose_count_panels(const LaunchCtx& lc, const Csr& X, int64_t nnz, int row_begin, int row_end,
+                                          int panel_w, int32_t* d_counts) {
+    const int rows = row_end - row_begin;
+    if (rows <= 0) return cudaSuccess;
+    if (nnz >= (int64_t)48 * X.rows)
+        k_transpose_count_panels<32><<<(rows + 7) / 8, 256, 0, lc.stream>>>(X, row_begin, row_end, panel_w, d_counts);
+    else
+        k_transpose_count_panels<8><<<(rows + 31) / 32, 256, 0, lc.stream>>>(X, row_begin, row_end, panel_w, d_counts);
+    SB_LAUNCH_CHECK(lc);
+    return cudaSuccess;
+}
+cudaError_t launch_transpose_fill_panels(const LaunchCtx& lc, const Csr& X, int64_t nnz, int row_begin, int row_end,
+                                         int panel_w, const int32_t* t_ptr, int32_t* d_cursor, int32_t* t_idx,
+                                         double* t_val) {
+    const int rows = row_end - row_begin;
+    if (rows <= 0) return cudaSuccess;
+    if (nnz >= (int64_t)48 * X.rows)
+        k_transpose_fill_panels<32><<<(rows + 7) / 8, 256, 0, lc.stream>>>(X, row_begin, row_end, panel_w, t_ptr, d_cursor, t_idx, t_val);
+    else
+        k_transpose_fill_panels<8><<<(rows + 31) / 32, 256, 0, lc.stream>>>(X, row_begin, row_end, panel_w, t_ptr, d_cursor, t_idx, t_val);
+    SB_LAUNCH_CHECK(lc);
+    return cudaSuccess;
+}
+
 cudaError_t launch_transpose_count(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_counts) {
     if (nnz <= 0) return cudaSuccess;
     k_transpose_count<<<(unsigned)((nnz + 255) / 256), 256, 0, lc.stream>>>(X.idx, nnz, d_counts);
@@ -430,13 +499,15 @@ cudaError_t launch_narrow_indptr(const LaunchCtx& lc, const int64_t* in, int32_t
 // Cost of row i of the triple product H Q H^T for the flop-balanced multi-GPU split:
 //   P1_i = sum over (i,j) in H of nnz(Q[j,:])                         (expansion of H[i,:] Q)
 //   P2_i = sum over those (j,c) of nnz(H^T[c,:])                      (entries of H^T the contraction streams)
-// cost_i = a * P1_i + b * P2_i + c * P2_i * (n - i) / n: every product pays its gathers of Q and of the extent of
-// its row of H^T (a), every entry of that row is read and tested against the diagonal (b), and the fraction
+// cost_i = a * P1_i * panels(i) + b * P2_i + c * P2_i * (n - i) / n: every product pays its gathers of Q and of the
+// extent of its row of H^T once per column panel the row takes part in (a; upper mode: the panels right of the
+// diagonal), every entry of H^T in those panels is read and tested against the diagonal (b), and the fraction
 // (n - i) / n that survives the k >= i cut of the upper-triangle mode is multiplied and accumulated (c).
 // (a, b, c) are fitted to the per-rank kernel times of cfg 5 (profiles/r2); SPGEMM_B200_TRIPLE_COST="a,b,c"
 // overrides them.  One warp per row.
 __global__ void __launch_bounds__(256)
-k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, double ca, double cb, double cc, int64_t* __restrict__ costs) {
+k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, int np, int panel_w, double ca, double cb, double cc,
+               int64_t* __restrict__ costs) {
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= H.rows) return;
     long long p1 = 0, p2 = 0;
@@ -449,15 +520,18 @@ k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, double ca, double cb, doubl
     p2 = warp_sum(p2);
     if (lane_id() == 0) {
         const double keep = upper_only ? (double)(H.rows - row) / (double)H.rows : 1.0;
-        costs[row] = (long long)(ca * (double)p1 + cb * (double)p2 + cc * (double)p2 * keep);
+        const int panels = upper_only ? np - row / panel_w : np;
+        costs[row] = (long long)(ca * (double)p1 * (double)(panels > 1 ? panels : 1) + cb * (double)p2 * keep +
+                                 cc * (double)p2 * keep);
     }
 }
 cudaError_t launch_triple_costs(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool upper_only,
-                                int64_t* d_costs) {
+                                int np, int panel_w, int64_t* d_costs) {
     if (H.rows <= 0) return cudaSuccess;
     double ca = 4.0, cb = 1.0, cc = 2.0;
     if (const char* v = getenv("SPGEMM_B200_TRIPLE_COST")) sscanf(v, "%lf,%lf,%lf", &ca, &cb, &cc);
-    k_triple_costs<<<(H.rows + 7) / 8, 256, 0, lc.stream>>>(H, Q, Ht, upper_only ? 1 : 0, ca, cb, cc, d_costs);
+    k_triple_costs<<<(H.rows + 7) / 8, 256, 0, lc.stream>>>(H, Q, Ht, upper_only ? 1 : 0, np, panel_w > 0 ? panel_w : 1,
+                                                           ca, cb, cc, d_costs);
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
 }

@@ -661,15 +661,74 @@ int dense_rows(spgemm_b200_mat* a, spgemm_b200_mat* b_in, int upper_only, int r0
     return SPGEMM_B200_OK;
 }
 
-// rows [r0, r1) of H Q H^T into d_c ((r1-r0) x n); d_cnt: device u64[4], zeroed here (P1, P2, row ticket).
+// Paneled transpose of rows [plan.k0, n) of H (analysis.cu): one CSR with plan.np * H.cols rows.
+struct PanelT {
+    int32_t *ptr = nullptr, *idx = nullptr;
+    double* val = nullptr;
+};
+static void panels_release(PanelT& t) {
+    dfree(t.ptr); dfree(t.idx); dfree(t.val);
+    t = PanelT();
+}
+static int transpose_panels(const spgemm_b200_mat* h, const TriplePlan& plan, PanelT* out) {
+    Ctx& g = cx();
+    NvtxRange nv("spgemm_b200:transpose_panels");
+    const size_t trows = (size_t)plan.np * (size_t)h->cols;
+    if (trows + 1 > 0x7fffffffULL) return fail(SPGEMM_B200_ERR_OVERFLOW, "triple: panels x columns of H exceed 2^31");
+    PanelT t;
+    int32_t *counts = nullptr, *cursor = nullptr;
+    int64_t* tmp = nullptr;
+    int rc;
+    if ((rc = dalloc(&t.ptr, trows + 1)) || (rc = dalloc(&t.idx, (size_t)h->nnz)) || (rc = dalloc(&t.val, (size_t)h->nnz)) ||
+        (rc = dalloc(&counts, trows + 1)) || (rc = dalloc(&cursor, trows + 1)) || (rc = dalloc(&tmp, 1032))) {
+        panels_release(t); dfree(counts); dfree(cursor); dfree(tmp);
+        return rc;
+    }
+    LaunchCtx lc = lctx();
+    cudaError_t e = cudaMemsetAsync(counts, 0, (trows + 1) * 4, g.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(cursor, 0, (trows + 1) * 4, g.stream);
+    if (e == cudaSuccess) e = launch_transpose_count_panels(lc, view(h), h->nnz, plan.k0, h->rows, plan.panel_w, counts);
+    if (e == cudaSuccess) e = launch_scan_i32(lc, counts, t.ptr, (int)trows, tmp);
+    if (e == cudaSuccess)
+        e = launch_transpose_fill_panels(lc, view(h), h->nnz, plan.k0, h->rows, plan.panel_w, t.ptr, cursor, t.idx, t.val);
+    dfree(counts); dfree(cursor); dfree(tmp);
+    if (e != cudaSuccess) {
+        panels_release(t);
+        return fail(SPGEMM_B200_ERR_CUDA, "paneled transpose", e);
+    }
+    *out = t;
+    return SPGEMM_B200_OK;
+}
+
+// rows [r0, r1) of H Q H^T into d_c ((r1-r0) x n); d_cnt: device u64[4], zeroed here (P1, P2, ticket, spare).
 int triple_rows(const spgemm_b200_mat* h, const spgemm_b200_mat* q, const spgemm_b200_mat* ht, int upper_only, int r0,
                 int r1, double* d_c, unsigned long long* d_cnt) {
     Ctx& g = cx();
-    NvtxRange nv("spgemm_b200:triple");
+    const int mode = env_mode("SPGEMM_B200_TRIPLE_MODE");
     cudaError_t e = cudaMemsetAsync(d_cnt, 0, 32, g.stream);
-    if (e == cudaSuccess)
-        e = launch_triple(lctx(), view(h), view(q), view(ht), ht->desc_sorted, upper_only != 0, r0, r1 - r0, d_c, d_cnt,
-                          ht->nnz, env_mode("SPGEMM_B200_TRIPLE_MODE"));
+    if (e != cudaSuccess) return fail(SPGEMM_B200_ERR_CUDA, "triple counters", e);
+    int rc;
+    if (mode == 2) {                                          // round-1 kernel on the plain transpose
+        spgemm_b200_mat* own = nullptr;
+        if (!ht) {
+            if ((rc = transpose_impl(h, &own, true))) return rc;
+            ht = own;
+        }
+        mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
+        NvtxRange nv("spgemm_b200:triple");
+        e = launch_triple_red(lctx(), view(h), view(q), view(ht), ht->desc_sorted, upper_only != 0, r0, r1 - r0, d_c, d_cnt);
+        mat_release(own);
+    } else {
+        TriplePlan plan = triple_plan(h->rows, r0, upper_only != 0, h->nnz, h->cols);
+        PanelT t;
+        const bool borrow = ht && plan.np == 1;               // one panel: a plain transpose serves as it is
+        if (!borrow && (rc = transpose_panels(h, plan, &t))) return rc;
+        mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
+        NvtxRange nv("spgemm_b200:triple");
+        e = launch_triple_panels(lctx(), view(h), view(q), borrow ? ht->ptr : t.ptr, borrow ? ht->idx : t.idx,
+                                 borrow ? ht->val : t.val, plan, upper_only != 0, r0, r1 - r0, d_c, d_cnt);
+        panels_release(t);
+    }
     if (e != cudaSuccess) return fail(SPGEMM_B200_ERR_CUDA, "triple kernel", e);
     g.stats.nnz_c = (int64_t)(r1 - r0) * h->rows;
     g.stats.bytes_min = 2 * csr_bytes(h->rows, h->nnz) + csr_bytes(q->rows, q->nnz) + 8 * g.stats.nnz_c;
@@ -684,7 +743,8 @@ int row_costs_impl(const spgemm_b200_mat* a, const spgemm_b200_mat* b, const spg
     cudaError_t e = cudaSuccess;
     int32_t* ws = nullptr;
     if (q) {
-        e = launch_triple_costs(lc, view(a), view(q), view(b), upper_only != 0, costs);
+        const TriplePlan plan = triple_plan(a->rows, 0, upper_only != 0, a->nnz, a->cols);
+        e = launch_triple_costs(lc, view(a), view(q), view(b), upper_only != 0, plan.np, plan.panel_w, costs);
     } else {
         int rc = dalloc(&ws, (size_t)m + (size_t)SYM_BINS * m + 32);
         if (rc) return rc;
@@ -1040,14 +1100,8 @@ int spgemm_b200_triple_dev(const spgemm_b200_mat* h, const spgemm_b200_mat* q, c
     int rc;
     if ((rc = ensure_checked(const_cast<spgemm_b200_mat*>(h), const_cast<spgemm_b200_mat*>(q)))) return rc;
     if (ht && (rc = ensure_checked(const_cast<spgemm_b200_mat*>(ht)))) return rc;
-    spgemm_b200_mat* own_ht = nullptr;
-    if (!ht) {
-        if ((rc = transpose_impl(h, &own_ht, env_mode("SPGEMM_B200_TRIPLE_MODE") == 2))) return rc;
-        ht = own_ht;
-    }
-    mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
     unsigned long long* d_cnt = nullptr;
-    if ((rc = dalloc(&d_cnt, 4))) { mat_release(own_ht); return rc; }
+    if ((rc = dalloc(&d_cnt, 4))) return rc;
     rc = triple_rows(h, q, ht, upper_only, row_begin, row_end, d_c, d_cnt);
     mark(EV_NUMERIC); mark(EV_POST);
     unsigned long long* hc = reinterpret_cast<unsigned long long*>(static_cast<char*>(g.h_small) + 512);
@@ -1056,7 +1110,6 @@ int spgemm_b200_triple_dev(const spgemm_b200_mat* h, const spgemm_b200_mat* q, c
     mark(EV_D2H);
     if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
     dfree(d_cnt);
-    mat_release(own_ht);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(SPGEMM_B200_ERR_CUDA, "triple kernel", e);
     g.stats.products = (int64_t)(hc[0] + hc[1]);
@@ -1074,12 +1127,12 @@ int spgemm_b200_triple(int n, int k, const int32_t* h_indptr, const int32_t* h_i
     ENTER_DEFAULT();
     Ctx& g = cx();
     begin_call();
-    spgemm_b200_mat *h = nullptr, *q = nullptr, *ht = nullptr;
+    spgemm_b200_mat *h = nullptr, *q = nullptr;
     double* d_c = nullptr;
     unsigned long long* d_cnt = nullptr;
     auto done = [&](int code) {
         dfree(d_c); dfree(d_cnt);
-        mat_release(h); mat_release(q); mat_release(ht);
+        mat_release(h); mat_release(q);
         return code;
     };
     {
@@ -1089,12 +1142,10 @@ int spgemm_b200_triple(int n, int k, const int32_t* h_indptr, const int32_t* h_i
         mark(EV_H2D);
     }
     if ((rc = ensure_checked(h, q))) return done(rc);
-    if ((rc = transpose_impl(h, &ht, env_mode("SPGEMM_B200_TRIPLE_MODE") == 2))) return done(rc);
-    mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
     const size_t elems = (size_t)n * (size_t)n;
     if ((rc = dalloc(&d_c, elems)) || (rc = dalloc(&d_cnt, 4))) return done(rc);
     const bool upper = mode != SPGEMM_B200_TRIPLE_REF_FULL;
-    if ((rc = triple_rows(h, q, ht, upper, 0, n, d_c, d_cnt))) return done(rc);
+    if ((rc = triple_rows(h, q, nullptr, upper, 0, n, d_c, d_cnt))) return done(rc);
     mark(EV_NUMERIC);
     cudaError_t e = cudaSuccess;
     if (mode == SPGEMM_B200_TRIPLE_REF_FULL) e = launch_symmetrize(lctx(), d_c, n);

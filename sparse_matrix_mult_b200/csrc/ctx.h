@@ -126,6 +126,8 @@ int ensure_checked(spgemm_b200_mat* m1, spgemm_b200_mat* m2 = nullptr);
 int sorted_view(spgemm_b200_mat* m, spgemm_b200_mat** out);
 int csr_impl(spgemm_b200_mat* a, spgemm_b200_mat* b, int upper_only, int r0, int r1, spgemm_b200_result** out);
 int dense_rows(spgemm_b200_mat* a, spgemm_b200_mat* b, int upper_only, int r0, int r1, double* d_c);
+// rows [r0, r1) of H Q H^T into d_c.  Builds the paneled transpose of H it needs (or uses `ht`, a plain transpose of
+// H, when one panel is enough); records EV_ANALYSIS / EV_SYMBOLIC before the kernel.  d_cnt: device u64[4].
 int triple_rows(const spgemm_b200_mat* h, const spgemm_b200_mat* q, const spgemm_b200_mat* ht, int upper_only, int r0,
                 int r1, double* d_c, unsigned long long* d_cnt);
 int row_costs_impl(const spgemm_b200_mat* a, const spgemm_b200_mat* b, const spgemm_b200_mat* q, int upper_only,

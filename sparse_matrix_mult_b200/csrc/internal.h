@@ -57,6 +57,14 @@ cudaError_t launch_transpose_count(const LaunchCtx& lc, const Csr& X, int64_t nn
 cudaError_t launch_transpose_fill(const LaunchCtx& lc, const Csr& X, int64_t nnz, const int32_t* t_ptr,
                                   int32_t* d_cursor, int32_t* t_idx, double* t_val);
 
+// paneled transpose of rows [row_begin, row_end) of X (see analysis.cu): counts / t_ptr / cursor have np * X.cols (+1)
+// entries, np = ceil((row_end - row_begin) / panel_w)
+cudaError_t launch_transpose_count_panels(const LaunchCtx& lc, const Csr& X, int64_t nnz, int row_begin, int row_end,
+                                          int panel_w, int32_t* d_counts);
+cudaError_t launch_transpose_fill_panels(const LaunchCtx& lc, const Csr& X, int64_t nnz, int row_begin, int row_end,
+                                         int panel_w, const int32_t* t_ptr, int32_t* d_cursor, int32_t* t_idx,
+                                         double* t_val);
+
 // rows sorted by column (ascending or descending), in place, any row length; d_long_list: int32[rows + 1] scratch
 cudaError_t launch_sort_rows(const LaunchCtx& lc, int rows, const int32_t* ptr, int32_t* idx, double* val,
                              int32_t* d_long_list, bool descending);
@@ -64,7 +72,7 @@ cudaError_t launch_narrow_indptr(const LaunchCtx& lc, const int64_t* in, int32_t
 
 // cost model of the triple product rows (see spgemm_b200_row_costs)
 cudaError_t launch_triple_costs(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool upper_only,
-                                int64_t* d_costs);
+                                int np, int panel_w, int64_t* d_costs);
 
 // ---- spgemm_sparse.cu ---------------------------------------------------------------------------
 struct SparseJob {
@@ -92,12 +100,19 @@ cudaError_t launch_symmetrize(const LaunchCtx& lc, double* d_c, int n);
 cudaError_t dense_kernels_configure();
 
 // ---- triple.cu ----------------------------------------------------------------------------------
-// ht_desc: every row of Ht is sorted by descending column (false = unknown -> every entry is filtered);
-// ht_nnz picks the lanes per row of H^T; mode 0 = shared-memory window kernel, 2 = round-1 L2-reduction kernel
-cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool ht_desc,
-                          bool upper_only, int row_begin, int nrows, double* d_c,
-                          unsigned long long* d_counters /* [3], zeroed: P1, P2, row ticket */, int64_t ht_nnz,
-                          int mode);
+// Column panels of C = H Q H^T (see k_triple_panels): np panels of panel_w columns starting at column k0.
+struct TriplePlan {
+    int k0, np, panel_w;
+};
+TriplePlan triple_plan(int n, int row_begin, bool upper_only, int64_t h_nnz, int h_cols);
+// t_ptr / t_idx / t_val: paneled transpose of rows [plan.k0, n) of H (launch_transpose_*_panels)
+cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q, const int32_t* t_ptr,
+                                 const int32_t* t_idx, const double* t_val, const TriplePlan& plan, bool upper_only,
+                                 int row_begin, int nrows, double* d_c,
+                                 unsigned long long* d_counters /* [4], zeroed: P1, P2, ticket, spare */);
+// round-1 kernel on the plain transpose Ht (ht_desc: its rows are sorted by descending column)
+cudaError_t launch_triple_red(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool ht_desc,
+                              bool upper_only, int row_begin, int nrows, double* d_c, unsigned long long* d_counters);
 cudaError_t triple_kernels_configure();
 
 }  // namespace sb

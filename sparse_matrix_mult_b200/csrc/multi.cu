@@ -117,7 +117,7 @@ void worker(Job* job, int d) {
         mark(EV_H2D);
     }
     if (!rc) rc = ensure_checked(a, b);
-    if (!rc && job->kind == K_TRIPLE) rc = transpose_impl(a, &ht, false);
+    if (!rc && d == 0 && job->kind == K_TRIPLE) rc = transpose_impl(a, &ht, false);   // row lengths of H^T for the costs
     if (!rc && d == 0) {
         std::vector<int64_t> costs((size_t)m);
         rc = dalloc(&d_costs, (size_t)m);
@@ -144,11 +144,11 @@ void worker(Job* job, int d) {
             if (!rc) job->res->parts[d] = part;
             mark(EV_POST); mark(EV_D2H);
         } else if (r1 > r0) {
-            mark(EV_SYMBOLIC);
+            if (job->kind != K_TRIPLE) mark(EV_SYMBOLIC);
             rc = dalloc(&d_c, (size_t)(r1 - r0) * (size_t)n);
             if (!rc && job->kind == K_TRIPLE) {
                 rc = dalloc(&d_cnt, 4);
-                if (!rc) rc = triple_rows(a, b, ht, job->upper_only, r0, r1, d_c, d_cnt);
+                if (!rc) rc = triple_rows(a, b, nullptr, job->upper_only, r0, r1, d_c, d_cnt);
             } else if (!rc) {
                 rc = dense_rows(a, b, job->upper_only, r0, r1, d_c);
             }

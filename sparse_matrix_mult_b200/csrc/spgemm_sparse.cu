@@ -492,9 +492,11 @@ void numeric_hash_caps(int cols, int* cap_h4k, int* cap_h12k) {
     const HashPlan p = hash_plan(cols);
     *cap_h4k = p.narrow ? kHashCap4K : kHashCapWide;
     *cap_h12k = p.narrow ? kHashCap12K : 0;
-    if (const char* v = getenv("SPGEMM_B200_NO_HASH_BINS")) {          // experiments: everything to the rank bin
-        if (atoi(v)) { *cap_h4k = 0; *cap_h12k = 0; }
-    }
+    // experiments: SPGEMM_B200_HASH_BINS bit 0 = 4,096-slot bin, bit 1 = 12,288-slot bin (others go to the rank bin)
+    int bins = 3;
+    if (const char* v = getenv("SPGEMM_B200_HASH_BINS")) bins = atoi(v);
+    if (!(bins & 1)) *cap_h4k = 0;
+    if (!(bins & 2)) *cap_h12k = 0;
 }
 
 // Run up to three independent bin kernels on side streams: fork after everything queued on the main stream so

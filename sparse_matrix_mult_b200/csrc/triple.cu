@@ -7,11 +7,9 @@
 // C[i,k] += w * h_kc for k >= i.  Work is P1 + P2 instead of n^2/2 * nnz/row, H Q is never
 // materialised, and every byte of C is written once.
 //
-// k_triple_window (default): the row's accumulator lives in SHARED memory -- a window of up to ~26,800 doubles
-// starting at the diagonal; columns beyond the window (only the first rows of very wide outputs have any) are
-// accumulated with float64 reductions that resolve in L2.  Shared-memory accumulation runs at 2-3x the chip-wide
-// L2 reduction rate (scripts/micro/atomic_bw.cu: 540 vs 197 G adds/s), needs no L2 residency of the C rows in
-// flight, and the finished window leaves with coalesced 128-bit streaming stores.
+// k_triple_panels (default): C is built one column panel at a time; a block owns a (panel, row) segment of up to
+// ~26,800 doubles in SHARED memory, so every add is a shared-memory add (scripts/micro/atomic_bw.cu: 540 G float64
+// adds/s chip-wide against 197 G/s for L2 reductions), and the slice of H^T a panel gathers from stays in L2.
 // k_triple_rows_red (round 1, kept selectable for A/B runs: SPGEMM_B200_TRIPLE_MODE=2): every add is an L2 reduction.
 #include <cstdlib>
 
@@ -58,60 +56,50 @@ __device__ __forceinline__ void triple_flush_counters(unsigned long long p1, uns
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Shared-memory window kernel.
+// Paneled shared-memory kernel.
 //
-// Per row i of C:
+// C is computed one COLUMN PANEL at a time (TriplePlan: np panels of panel_w columns starting at column k0).  The
+// contraction of panel p only needs the entries (k, h_kc) of H^T with k inside the panel -- the p-th part of the
+// paneled transpose (analysis.cu), a few tens of MB -- so its gathers hit L2, where the whole H^T (cfg 5: 96 MB
+// against ~63 MB of effective L2 for data shared by both dies) made every second gather a DRAM access (round 1:
+// 36 GB of DRAM reads, L2 hit rate 50 %, long-scoreboard stalls dominant).  The price is that the expansion
+// H[i,:] Q is redone for every panel a row takes part in (upper mode: the panels right of the diagonal), which is
+// a coalesced stream of rows of Q.  A panel is at most as wide as the shared-memory accumulator, so every add is a
+// shared-memory add and the finished segment leaves with coalesced 128-bit streaming stores.
+//
+// Work items are (panel, row) pairs handed out panel-major through an atomic ticket.  Per item:
 //   1. up to blockDim entries (j, h_ij) of H[i,:] are loaded one per thread together with the extent of row j of Q;
-//      a block-wide prefix sum numbers the products of the expansion 0..total-1;
-//   2. the products are taken 32 at a time by the warps, round-robin IN ORDER (chunk k goes to warp k mod nwarp):
-//      lane l of a warp takes product 32k + l, finds its row of Q in the prefix table, loads (c, q_jc) -- coalesced,
-//      a row of Q is contiguous, and streamed past L2 (evict-first: a row of Q is used once per row of C) -- and
-//      the extent of row c of H^T;
+//      a block-wide prefix sum numbers the products of the expansion 0..total-1; every warp takes an equal
+//      contiguous share of them, 32 per step;
+//   2. software pipeline over the steps of a warp: the loads of (c, q_jc) for step s+2 and of the extent of row c
+//      of H^T for step s+1 are in flight while step s is contracted (three dependent memory latencies overlapped);
 //   3. contraction as ONE flat stream: the rows of H^T of the warp's 32 products are numbered by a warp prefix sum
-//      of their lengths and the warp walks the concatenation 32 entries per step.  The owner of an entry is found
-//      from a 32-bit mask of the row starts inside the step (one warp-wide OR reduction + popcount); its weight
-//      w = h_ij * q_jc and the offset of its row come from a 32-entry per-warp table in shared memory.  When
-//      consecutive products have consecutive c (banded Q) their rows of H^T are adjacent in memory, so every load
-//      of the stream is fully coalesced; for any other Q it is a balanced gather.  Every lane is active whatever
-//      the row lengths of H^T (the round-1 kernel walked one row per thread: 17.8 of 32 lanes active);
-//   4. entries with k >= i (upper mode) are added to the shared window [w0, w1) (float64 CAS loop) or, beyond it,
-//      to C itself (L2 reduction);
-//   5. the window is streamed out and cleared in one pass.
-//
-// SYNC (cooperative launch): the grid processes the rows in batches of gridDim.x, one row per block, with a grid
-// barrier between batches.  Rows of H are sorted by column and step 2 walks them in order, so all blocks sweep the
-// column range of H^T together: at any moment the chip reads a narrow band of H^T (cfg 5: ~20 MB of the 96 MB),
-// which stays L2 resident, instead of gathering from all of it (round 1: 36 GB of DRAM reads, L2 hit rate 50 %).
-// Without SYNC rows are handed out through an atomic ticket.
+//      of their lengths and the warp walks the concatenation 128 entries at a time (four independent loads per
+//      lane in flight).  The owner of an entry is found from a 32-bit mask of the row starts inside the step (one
+//      warp-wide OR reduction + popcount); its weight w = h_ij q_jc and the offset of its row come from a 32-entry
+//      per-warp table in shared memory.  Consecutive products with consecutive c (banded Q) have adjacent rows of
+//      H^T, so the stream is coalesced; for any other Q it is a balanced gather.  Every lane is busy whatever the
+//      row lengths of H^T (round 1 walked one row per thread: 17.8 of 32 lanes active);
+//   4. entries with k >= i (upper mode) are added into the shared segment (float64 CAS loop);
+//   5. the segment is streamed out and cleared in one pass.
 //
 // Dynamic shared memory: acc[win_cap] | hv[nt] | w[nt] | qs[nt] | pre[nt + 1] | d[nt].
 struct TripleScratch {
     unsigned red[33];
     unsigned long long cnt[2];
-    int row;
+    int item;
 };
 __host__ __device__ inline size_t triple_window_smem(int win_cap, int threads) {
     return (size_t)win_cap * 8 + (size_t)threads * 28 + 16;
 }
 
-__device__ __forceinline__ int ld_stream_i32(const int32_t* p) { return __ldcs(p); }
-__device__ __forceinline__ double ld_stream_f64(const double* p) { return __ldcs(p); }
+struct StepA { int c; double qv, hv; };          // c < 0: no product in this lane
+struct StepB { int hs, he; double w; };          // hs == he: nothing to contract
 
-// counters[3]: monotone arrival counter of the grid barrier (zeroed before the launch)
-__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1ULL);
-        while (*((volatile unsigned long long*)counter) < target) { }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-template <bool UPPER, bool SYNC>
+template <bool UPPER>
 __global__ void __launch_bounds__(1024, 1)
-k_triple_window(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, int win_cap,
+k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int32_t* __restrict__ t_idx,
+                const double* __restrict__ t_val, TriplePlan plan, int row_begin, int nrows, int win_cap,
                 double* __restrict__ C, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ TripleScratch S;
@@ -128,118 +116,166 @@ k_triple_window(Csr H, Csr Q, Csr Ht, int row_begin, int nrows, int win_cap,
     if (tid < 2) S.cnt[tid] = 0;
     for (int t = tid; t < win_cap; t += nt) acc[t] = 0.0;
     __syncthreads();
-    unsigned long long p1 = 0;
-    unsigned p2 = 0;
-    unsigned long long p2_total = 0;
-    const int nbatch = SYNC ? (nrows + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    for (int batch = 0; ; ++batch) {
-        int r;
-        if (SYNC) {
-            if (batch >= nbatch) break;
-            r = batch * (int)gridDim.x + (int)blockIdx.x;
-        } else {
-            if (tid == 0) S.row = (int)atomicAdd(counters + 2, 1ULL);
-            __syncthreads();
-            r = S.row;
-            __syncthreads();
-            if (r >= nrows) break;
+    unsigned long long p1 = 0, p2_total = 0;
+    while (true) {
+        if (tid == 0) S.item = (int)atomicAdd(counters + 2, 1ULL);
+        __syncthreads();
+        int item = S.item;
+        __syncthreads();
+        // item -> (panel, local row): panel p serves the rows above the end of the panel (upper mode) or all rows
+        int p = 0, rows_p = 0;
+        for (; p < plan.np; ++p) {
+            const int p_end = min(n, plan.k0 + (p + 1) * plan.panel_w);
+            rows_p = UPPER ? max(0, min(nrows, p_end - row_begin)) : nrows;
+            if (item < rows_p) break;
+            item -= rows_p;
         }
-        if (r < nrows) {
-            const int i = row_begin + r;
-            const int lo = UPPER ? i : 0;
-            const int w0 = lo, w1 = min(n, lo + win_cap);
-            double* row = C + (size_t)r * n;
-            const int h_begin = __ldg(H.ptr + i), h_end = __ldg(H.ptr + i + 1);
-            // zeros left of the diagonal (never touched again: evict-first) and right of the window (about to take
-            // reductions: default policy so the lines stay in L2)
-            triple_stream_out(row, nullptr, w0);
-            for (int t = w1 + tid; t < n; t += nt) row[t] = 0.0;
-            for (int base = h_begin; base < h_end; base += nt) {
-                const int cnt = min(nt, h_end - base);
-                unsigned len = 0;
-                if (tid < cnt) {
-                    const int j = __ldg(H.idx + base + tid);
-                    const int qs = __ldg(Q.ptr + j);
-                    len = (unsigned)(__ldg(Q.ptr + j + 1) - qs);
-                    s_hv[tid] = __ldg(H.val + base + tid);
-                    s_qs[tid] = qs;
-                }
-                unsigned total;
-                const unsigned ex = block_excl_scan<unsigned>(len, S.red, &total);
-                if (tid < cnt) s_pre[tid] = ex;
-                if (tid == 0) s_pre[cnt] = total;
-                __syncthreads();                           // tables complete; tail zeros ordered before reductions
-                if (tid == 0) p1 += total;
-                for (unsigned f0 = (unsigned)warp * 32u; f0 < total; f0 += (unsigned)nwarp * 32u) {
-                    const unsigned f = f0 + lane;
-                    const bool valid = f < total;
-                    int hs = 0;
-                    unsigned hlen = 0;
-                    double w = 0.0;
-                    if (valid) {
-                        int a = 0, b = cnt;                // largest a with pre[a] <= f  (pre[cnt] = total > f)
-                        while (b - a > 1) {
-                            const int mid = (a + b) >> 1;
-                            if (s_pre[mid] <= f) a = mid; else b = mid;
-                        }
-                        const int q = s_qs[a] + (int)(f - s_pre[a]);
-                        const int c = ld_stream_i32(Q.idx + q);
-                        w = s_hv[a] * ld_stream_f64(Q.val + q);
-                        hs = __ldg(Ht.ptr + c);
-                        hlen = (unsigned)(__ldg(Ht.ptr + c + 1) - hs);
+        if (p >= plan.np) break;
+        const int r = item, i = row_begin + r;
+        const int p0 = plan.k0 + p * plan.panel_w, p1c = min(n, p0 + plan.panel_w);
+        const int lo = UPPER ? max(i, p0) : p0;                    // first column of the segment
+        const bool first_panel = UPPER ? (i >= p0) : (p == 0);     // the panel that holds the diagonal of row i
+        double* row = C + (size_t)r * n;
+        const int32_t* hp = t_ptr + (size_t)p * H.cols;
+        const int h_begin = __ldg(H.ptr + i), h_end = __ldg(H.ptr + i + 1);
+        // zeros left of the covered columns: below the diagonal (upper mode) / left of column k0
+        if (first_panel) triple_stream_out(row, nullptr, UPPER ? lo : plan.k0);
+        unsigned p2 = 0;
+        for (int base = h_begin; base < h_end; base += nt) {
+            const int cnt = min(nt, h_end - base);
+            unsigned len = 0;
+            if (tid < cnt) {
+                const int j = __ldg(H.idx + base + tid);
+                const int qs = __ldg(Q.ptr + j);
+                len = (unsigned)(__ldg(Q.ptr + j + 1) - qs);
+                s_hv[tid] = __ldg(H.val + base + tid);
+                s_qs[tid] = qs;
+            }
+            unsigned total;
+            const unsigned ex = block_excl_scan<unsigned>(len, S.red, &total);
+            if (tid < cnt) s_pre[tid] = ex;
+            if (tid == 0) s_pre[cnt] = total;
+            __syncthreads();
+            if (tid == 0 && first_panel) p1 += total;
+            const unsigned wb = (unsigned)((unsigned long long)total * warp / nwarp);
+            const unsigned we = (unsigned)((unsigned long long)total * (warp + 1) / nwarp);
+            if (wb < we) {
+                int r_base;
+                {                                          // row of Q of the warp's first product
+                    int a = 0, b = cnt;
+                    while (b - a > 1) {
+                        const int mid = (a + b) >> 1;
+                        if (s_pre[mid] <= wb) a = mid; else b = mid;
                     }
-                    // flat numbering of the entries of the 32 rows of H^T
+                    r_base = a;
+                }
+                // stage A: which (j, c) is product f, issue the loads of c and q_jc (streamed: used once per row)
+                auto stage_a = [&](unsigned f0) {
+                    StepA o{-1, 0.0, 0.0};
+                    if (f0 >= we) return o;                // warp-uniform
+                    const unsigned f = f0 + lane;
+                    int rr = r_base;
+                    if (f < we) {
+                        if (s_pre[rr + 1] <= f) {          // beyond the base row: largest rr with pre[rr] <= f
+                            int a = rr + 1, b = cnt;
+                            while (b - a > 1) {
+                                const int mid = (a + b) >> 1;
+                                if (s_pre[mid] <= f) a = mid; else b = mid;
+                            }
+                            rr = a;
+                        }
+                        const int q = s_qs[rr] + (int)(f - s_pre[rr]);
+                        o.c = __ldcs(Q.idx + q);
+                        o.qv = __ldcs(Q.val + q);
+                        o.hv = s_hv[rr];
+                    }
+                    r_base = __shfl_sync(FULL, rr, (int)min(31u, we - f0 - 1u));
+                    return o;
+                };
+                // stage B: weight of the product, issue the loads of the extent of row c of this panel of H^T
+                auto stage_b = [&](const StepA& a) {
+                    StepB o{0, 0, 0.0};
+                    if (a.c >= 0) {
+                        o.w = a.hv * a.qv;
+                        o.hs = __ldg(hp + a.c);
+                        o.he = __ldg(hp + a.c + 1);
+                    }
+                    return o;
+                };
+                StepA sa = stage_a(wb);
+                StepB sb = stage_b(sa);
+                sa = stage_a(wb + 32u);
+                for (unsigned f0 = wb; f0 < we; f0 += 32u) {
+                    const StepB cur = sb;
+                    sb = stage_b(sa);
+                    sa = stage_a(f0 + 64u);
+                    // stage C: contraction of the 32 products of `cur`
+                    const unsigned hlen = (unsigned)(cur.he - cur.hs);
                     const unsigned incl = warp_incl_scan(hlen);
                     const unsigned pre = incl - hlen;
                     const unsigned L = __shfl_sync(FULL, incl, 31);
                     const unsigned nonempty = __ballot_sync(FULL, hlen > 0);
                     if (hlen > 0) {
                         const int rank = __popc(nonempty & lt_mask);
-                        s_w[rank] = w;
-                        s_d[rank] = hs - (int)pre;
+                        s_w[rank] = cur.w;
+                        s_d[rank] = cur.hs - (int)pre;
                     }
                     __syncwarp();
                     int heads_before = 0;
-                    for (unsigned eb = 0; eb < L; eb += 32) {
-                        const unsigned bit = (hlen > 0 && pre >= eb && pre < eb + 32) ? 1u << (pre - eb) : 0u;
-                        const unsigned heads = __reduce_or_sync(FULL, bit);
-                        const int owner = heads_before + __popc(heads & le_mask) - 1;
-                        heads_before += __popc(heads);
-                        const unsigned p = eb + lane;
-                        if (p < L) {
-                            const int addr = (int)p + s_d[owner];
-                            const int k = __ldg(Ht.idx + addr);
-                            if (k >= lo) {
-                                const double x = s_w[owner] * __ldg(Ht.val + addr);
-                                if (k < w1) atomicAdd(acc + (k - w0), x); else atomicAdd(row + k, x);
+                    for (unsigned eb = 0; eb < L; eb += 128u) {
+                        int addr[4], k[4];
+                        double wv[4], v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const unsigned e0 = eb + 32u * u;
+                            k[u] = -1;
+                            addr[u] = 0;
+                            wv[u] = 0.0;
+                            if (e0 < L) {                  // warp-uniform
+                                const unsigned bit = (hlen > 0 && pre >= e0 && pre < e0 + 32u) ? 1u << (pre - e0) : 0u;
+                                const unsigned heads = __reduce_or_sync(FULL, bit);
+                                const int owner = heads_before + __popc(heads & le_mask) - 1;
+                                heads_before += __popc(heads);
+                                const unsigned pp = e0 + lane;
+                                if (pp < L) {
+                                    addr[u] = (int)pp + s_d[owner];
+                                    wv[u] = s_w[owner];
+                                    k[u] = __ldg(t_idx + addr[u]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) v[u] = k[u] >= lo ? __ldg(t_val + addr[u]) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (k[u] >= lo) {
+                                atomicAdd(acc + (k[u] - lo), wv[u] * v[u]);
                                 ++p2;
                             }
                         }
                     }
-                    __syncwarp();                          // the per-warp tables are rewritten by the next chunk
+                    __syncwarp();                          // the per-warp tables are rewritten by the next step
                 }
-                __syncthreads();                           // tables are rewritten by the next slice / row
             }
-            p2_total += p2;
-            p2 = 0;
-            // window out (coalesced 128-bit streaming stores) and cleared for the next row
-            const int count = w1 - w0;
-            double* dst = row + w0;
-            const int head = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1);
-            if (head && tid == 0 && count > 0) { st_stream_f64(dst, acc[0]); acc[0] = 0.0; }
-            const int pairs = (count - head) >> 1;
-            double* d2 = dst + head;
-            double* s2 = acc + head;
-            for (int t = tid; t < pairs; t += nt) {
-                st_stream_f64x2(d2 + 2 * t, s2[2 * t], s2[2 * t + 1]);
-                s2[2 * t] = 0.0;
-                s2[2 * t + 1] = 0.0;
-            }
-            const int tail = head + 2 * pairs;
-            if (tail < count && tid == nt - 1) { st_stream_f64(dst + tail, acc[tail]); acc[tail] = 0.0; }
+            __syncthreads();                               // tables are rewritten by the next slice / item
         }
-        if (SYNC) grid_barrier(counters + 3, (unsigned long long)(batch + 1) * gridDim.x);
-        else __syncthreads();                              // clearing ordered before the next row's adds
+        p2_total += p2;
+        // segment out (coalesced 128-bit streaming stores) and cleared for the next item
+        const int count = p1c - lo;
+        double* dst = row + lo;
+        const int head = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1);
+        if (head && tid == 0 && count > 0) { st_stream_f64(dst, acc[0]); acc[0] = 0.0; }
+        const int pairs = (count - head) >> 1;
+        double* d2 = dst + head;
+        double* s2 = acc + head;
+        for (int t = tid; t < pairs; t += nt) {
+            st_stream_f64x2(d2 + 2 * t, s2[2 * t], s2[2 * t + 1]);
+            s2[2 * t] = 0.0;
+            s2[2 * t + 1] = 0.0;
+        }
+        const int tail = head + 2 * pairs;
+        if (tail < count && tid == nt - 1) { st_stream_f64(dst + tail, acc[tail]); acc[tail] = 0.0; }
+        // (the ticket barriers at the top of the loop order the clearing before the next item's adds)
     }
     triple_flush_counters(p1, p2_total, S.cnt, counters);
 }
@@ -289,12 +325,6 @@ k_triple_rows_red(Csr H, Csr Q, Csr Ht, int ht_desc, int row_begin, int nrows,
 // ---------------------------------------------------------------------------------------------------
 static size_t g_triple_smem_optin = 0, g_triple_smem_sm = 0;
 
-template <bool UPPER, bool SYNC>
-static cudaError_t configure_window() {
-    return cudaFuncSetAttribute(k_triple_window<UPPER, SYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(g_triple_smem_optin - sizeof(TripleScratch) - 64));
-}
-
 cudaError_t triple_kernels_configure() {
     int dev = 0, optin = 0, per_sm = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -305,10 +335,10 @@ cudaError_t triple_kernels_configure() {
     if (e != cudaSuccess) return e;
     g_triple_smem_optin = (size_t)optin;
     g_triple_smem_sm = (size_t)per_sm;
-    if ((e = configure_window<true, true>()) != cudaSuccess) return e;
-    if ((e = configure_window<true, false>()) != cudaSuccess) return e;
-    if ((e = configure_window<false, true>()) != cudaSuccess) return e;
-    return configure_window<false, false>();
+    const int dyn = (int)(g_triple_smem_optin - sizeof(TripleScratch) - 64);
+    e = cudaFuncSetAttribute(k_triple_panels<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_triple_panels<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -316,79 +346,94 @@ static int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-template <bool UPPER, bool SYNC>
-static cudaError_t launch_window(int grid, int threads, size_t smem, cudaStream_t st, Csr H, Csr Q, Csr Ht, int row_begin,
-                                 int nrows, int win_cap, double* d_c, unsigned long long* d_counters) {
-    if (!SYNC) {
-        k_triple_window<UPPER, false><<<grid, threads, smem, st>>>(H, Q, Ht, row_begin, nrows, win_cap, d_c, d_counters);
-        return cudaGetLastError();
-    }
-    void* args[] = {&H, &Q, &Ht, &row_begin, &nrows, &win_cap, &d_c, &d_counters};
-    return cudaLaunchCooperativeKernel((const void*)k_triple_window<UPPER, true>, dim3(grid), dim3(threads), args, smem, st);
+static int triple_cap_max() {
+    return (int)(((g_triple_smem_optin - sizeof(TripleScratch) - 64 - triple_window_smem(0, 1024)) / 8) & ~(size_t)1);
 }
 
-cudaError_t launch_triple(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool ht_desc,
-                          bool upper_only, int row_begin, int nrows, double* d_c, unsigned long long* d_counters,
-                          int64_t ht_nnz, int mode) {
+// Panels of C for rows [row_begin, ...): as few as the shared-memory accumulator allows (a panel is one segment), more
+// when the part of H^T they gather from would not stay in L2 (SPGEMM_B200_TRIPLE_L2_MB, default 40: the data is shared
+// by the SMs of both dies, so about half of the 126 MB is usable); SPGEMM_B200_TRIPLE_PANELS forces a count.
+TriplePlan triple_plan(int n, int row_begin, bool upper_only, int64_t h_nnz, int h_cols) {
+    TriplePlan plan;
+    plan.k0 = upper_only ? row_begin : 0;
+    const int cover = n - plan.k0 > 0 ? n - plan.k0 : 1;
+    const int cap = triple_cap_max();
+    int np = (cover + cap - 1) / cap;
+    const double covered_bytes = 12.0 * (double)h_nnz * (double)cover / (double)(n > 0 ? n : 1);
+    const double budget = 1.0e6 * env_int("SPGEMM_B200_TRIPLE_L2_MB", 40) - 4.0 * (double)h_cols;
+    if (budget > 0) {
+        const int np_l2 = (int)(covered_bytes / budget) + 1;
+        if (np_l2 > np) np = np_l2;
+    }
+    if (np > 16) np = (cover + cap - 1) / cap > 16 ? (cover + cap - 1) / cap : 16;
+    const int forced = env_int("SPGEMM_B200_TRIPLE_PANELS", 0);
+    if (forced > 0 && forced >= (cover + cap - 1) / cap) np = forced;
+    if (np > cover) np = cover;
+    int w = (cover + np - 1) / np;
+    w = (w + 1) & ~1;                                   // even width: segments start 16-byte aligned in shared memory
+    plan.panel_w = w;
+    plan.np = (cover + w - 1) / w;
+    return plan;
+}
+
+cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q, const int32_t* t_ptr,
+                                 const int32_t* t_idx, const double* t_val, const TriplePlan& plan, bool upper_only,
+                                 int row_begin, int nrows, double* d_c, unsigned long long* d_counters) {
     const int n = H.rows;
     if (nrows <= 0 || n <= 0) return cudaSuccess;
-    if (mode == 2) {
-        const double l2_budget = 64.0e6;                                  // bytes of C rows in flight
-        const double row_bytes = 8.0 * n * (upper_only ? 0.6 : 1.0);      // upper rows touch [i, n) only
-        int rows_in_flight = (int)(l2_budget / row_bytes);
-        if (rows_in_flight < lc.sm_count) rows_in_flight = lc.sm_count;
-        const bool big = rows_in_flight < lc.sm_count * 4;                // few rows allowed: fat blocks
-        const int per_sm = big ? 1 : (rows_in_flight / lc.sm_count > 8 ? 8 : rows_in_flight / lc.sm_count);
-        int grid = lc.sm_count * per_sm;
-        if (grid > nrows) grid = nrows;
-        const int d = ht_desc ? 1 : 0;
-        if (big) {
-            if (upper_only)
-                k_triple_rows_red<true, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
-            else
-                k_triple_rows_red<false, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
-        } else {
-            if (upper_only)
-                k_triple_rows_red<true, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
-            else
-                k_triple_rows_red<false, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
-        }
-        SB_LAUNCH_CHECK(lc);
-        return cudaSuccess;
-    }
-    // ---- shared-memory window kernel ----
-    // window: the widest row segment this launch accumulates (row `row_begin` in upper mode), capped by what one
-    // block may hold; 1, 2 or 4 blocks per SM of 1024 / 512 / 256 threads (32 warps per SM at <= 64 registers)
     const size_t fixed = sizeof(TripleScratch) + 1024;                    // static scratch + per-block reserve
-    const int cap_max = (int)(((g_triple_smem_optin - sizeof(TripleScratch) - 64 - triple_window_smem(0, 1024)) / 8) & ~(size_t)1);
-    int need = upper_only ? n - row_begin : n;
-    need = (need + 1) & ~1;
-    if (need < 2) need = 2;
-    int win = need < cap_max ? need : cap_max;
-    if (const int o = env_int("SPGEMM_B200_TRIPLE_WIN", 0))              // experiments: force the window / residency
-        win = (o < cap_max ? o : cap_max) & ~1;
+    const int win = plan.panel_w;
+    // 1, 2 or 4 blocks per SM of 1024 / 512 / 256 threads (32 warps per SM at <= 64 registers)
     int per_sm = 1;
     for (int cand : {4, 2}) {
         if (g_triple_smem_sm / (triple_window_smem(win, 1024 / cand) + fixed) >= (size_t)cand) { per_sm = cand; break; }
     }
     const int threads = 1024 / per_sm;
+    int64_t items = 0;
+    for (int p = 0; p < plan.np; ++p) {
+        const int p_end = plan.k0 + (p + 1) * plan.panel_w < n ? plan.k0 + (p + 1) * plan.panel_w : n;
+        int rows_p = upper_only ? p_end - row_begin : nrows;
+        if (rows_p > nrows) rows_p = nrows;
+        if (rows_p > 0) items += rows_p;
+    }
+    int grid = lc.sm_count * per_sm;
+    if ((int64_t)grid > items) grid = (int)items;
+    if (grid < 1) grid = 1;
+    const size_t smem = triple_window_smem(win, threads);
+    if (upper_only)
+        k_triple_panels<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_idx, t_val, plan, row_begin, nrows, win, d_c, d_counters);
+    else
+        k_triple_panels<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_idx, t_val, plan, row_begin, nrows, win, d_c, d_counters);
+    SB_LAUNCH_CHECK(lc);
+    return cudaSuccess;
+}
+
+// Round-1 kernel (SPGEMM_B200_TRIPLE_MODE=2): Ht is the plain transpose of H.
+cudaError_t launch_triple_red(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool ht_desc,
+                              bool upper_only, int row_begin, int nrows, double* d_c, unsigned long long* d_counters) {
+    const int n = H.rows;
+    if (nrows <= 0 || n <= 0) return cudaSuccess;
+    const double l2_budget = 64.0e6;                                  // bytes of C rows in flight
+    const double row_bytes = 8.0 * n * (upper_only ? 0.6 : 1.0);      // upper rows touch [i, n) only
+    int rows_in_flight = (int)(l2_budget / row_bytes);
+    if (rows_in_flight < lc.sm_count) rows_in_flight = lc.sm_count;
+    const bool big = rows_in_flight < lc.sm_count * 4;                // few rows allowed: fat blocks
+    const int per_sm = big ? 1 : (rows_in_flight / lc.sm_count > 8 ? 8 : rows_in_flight / lc.sm_count);
     int grid = lc.sm_count * per_sm;
     if (grid > nrows) grid = nrows;
-    const size_t smem = triple_window_smem(win, threads);
-    // lock-step batches (grid barrier) pay when H^T is too big to stay in L2 whatever the order of the gathers
-    const double ht_bytes = 12.0 * (double)ht_nnz + 4.0 * (double)Ht.rows;
-    const bool sync = env_int("SPGEMM_B200_TRIPLE_SYNC", ht_bytes > 40.0e6 ? 1 : 0) != 0 && grid > 1;
-    cudaError_t e = cudaErrorUnknown;
-    if (sync) {
-        e = upper_only ? launch_window<true, true>(grid, threads, smem, lc.stream, H, Q, Ht, row_begin, nrows, win, d_c, d_counters)
-                       : launch_window<false, true>(grid, threads, smem, lc.stream, H, Q, Ht, row_begin, nrows, win, d_c, d_counters);
-        if (e != cudaSuccess) cudaGetLastError();          // not co-resident (another kernel holds SMs): ticket mode
+    const int d = ht_desc ? 1 : 0;
+    if (big) {
+        if (upper_only)
+            k_triple_rows_red<true, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
+        else
+            k_triple_rows_red<false, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
+    } else {
+        if (upper_only)
+            k_triple_rows_red<true, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
+        else
+            k_triple_rows_red<false, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
     }
-    if (e != cudaSuccess)
-        e = upper_only ? launch_window<true, false>(grid, threads, smem, lc.stream, H, Q, Ht, row_begin, nrows, win, d_c, d_counters)
-                       : launch_window<false, false>(grid, threads, smem, lc.stream, H, Q, Ht, row_begin, nrows, win, d_c, d_counters);
-    if (e != cudaSuccess) return e;
-    ++*lc.launches;
+    SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
 }
 

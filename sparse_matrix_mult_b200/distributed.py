@@ -39,8 +39,8 @@ def partition_by_cost(costs, parts):
 
 def host_row_costs(a, b, kind, upper_only):
     """Per-row cost on the host (numpy): products of A rows against B; for the triple product
-    a P1_i + b P2_i + c P2_i (n - i)/n with (a, b, c) = (4, 1, 2), the same model as k_triple_costs
-    (csrc/analysis.cu)."""
+    a P1_i + (b + c) P2_i (n - i)/n with (a, b, c) = (4, 1, 2): the one-panel case of k_triple_costs
+    (csrc/analysis.cu; the CPU tests only need a deterministic, monotone stand-in)."""
     blen = np.diff(b.indptr).astype(np.int64)
     rows = np.repeat(np.arange(a.shape[0]), np.diff(a.indptr))
     p1 = np.bincount(rows, weights=blen[a.indices], minlength=a.shape[0]).astype(np.float64)
@@ -57,7 +57,7 @@ def host_row_costs(a, b, kind, upper_only):
     if upper_only:
         n = a.shape[0]
         keep = (n - np.arange(n)) / max(1, n)
-    return 4.0 * p1 + 1.0 * p2 + 2.0 * p2 * keep
+    return 4.0 * p1 + 3.0 * p2 * keep
 
 
 # ------------------------------------------------------------------------------------------------------
