@@ -85,6 +85,8 @@ cudaError_t launch_row_products(const LaunchCtx& lc, const Csr& A, const Csr& B,
 // out-of-bounds device atomic).  A CSR has sorted rows iff every descent idx[q] > idx[q+1] sits on a row boundary.
 // flags[1] = descents anywhere, flags[2] = descents on row boundaries, flags[3] = invalid entries (column index
 // outside [0, cols), indptr not monotone / outside [0, nnz], indptr[0] != 0, indptr[rows] != nnz);
+// flags[4] = pairs with idx[q+1] != idx[q] + 1 anywhere, flags[5] = such pairs on row boundaries: every row is ONE
+// RUN of consecutive columns (a banded matrix) iff the two are equal;
 // flags[0] = rows sorted (set by k_sorted_flag).
 __global__ void __launch_bounds__(256)
 k_check_csr(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, int rows, int cols, int64_t nnz,
@@ -92,7 +94,7 @@ k_check_csr(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, in
     // entries: four per thread (one 128-bit load when aligned) plus the first entry of the next quad
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t q0 = t * 4;
-    int any = 0, edge = 0, bad = 0;
+    int any = 0, edge = 0, bad = 0, gap = 0, gap_edge = 0;
     if (q0 < nnz) {
         int c[5];
         if (q0 + 4 <= nnz && (reinterpret_cast<uintptr_t>(idx) & 15) == 0) {
@@ -107,7 +109,10 @@ k_check_csr(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, in
         for (int u = 0; u < 4; ++u) {
             if (q0 + u < nnz) {
                 bad |= c[u] < 0 || c[u] >= cols;
-                if (q0 + u + 1 < nnz) any += c[u] > c[u + 1];
+                if (q0 + u + 1 < nnz) {
+                    any += c[u] > c[u + 1];
+                    gap += c[u + 1] != c[u] + 1;
+                }
             }
         }
     }
@@ -115,16 +120,24 @@ k_check_csr(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, in
     if (t < rows) {
         const int s = __ldg(ptr + t), e = __ldg(ptr + t + 1);
         if (s < 0 || e < s || (int64_t)e > nnz) bad = 1;
-        else if (e > s && e < nnz) edge = __ldg(idx + e - 1) > __ldg(idx + e);
+        else if (e > s && e < nnz) {
+            const int last = __ldg(idx + e - 1), next = __ldg(idx + e);
+            edge = last > next;
+            gap_edge = next != last + 1;
+        }
         if (t == 0 && s != 0) bad = 1;
         if (t == rows - 1 && (int64_t)e != nnz) bad = 1;
     }
     any = warp_sum(any);
+    gap = warp_sum(gap);
     const unsigned m_edge = __ballot_sync(FULL, edge), m_bad = __ballot_sync(FULL, bad);
+    const unsigned m_gap_edge = __ballot_sync(FULL, gap_edge);
     if (lane_id() == 0) {
         if (any) atomicAdd(flags + 1, any);
         if (m_edge) atomicAdd(flags + 2, __popc(m_edge));
         if (m_bad) atomicAdd(flags + 3, __popc(m_bad));
+        if (gap) atomicAdd(flags + 4, gap);
+        if (m_gap_edge) atomicAdd(flags + 5, __popc(m_gap_edge));
     }
 }
 __global__ void k_sorted_flag(int32_t* __restrict__ flags) {
@@ -132,7 +145,7 @@ __global__ void k_sorted_flag(int32_t* __restrict__ flags) {
 }
 
 cudaError_t launch_check_csr(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_flags) {
-    cudaError_t e = cudaMemsetAsync(d_flags, 0, 4 * sizeof(int32_t), lc.stream);
+    cudaError_t e = cudaMemsetAsync(d_flags, 0, 8 * sizeof(int32_t), lc.stream);
     if (e != cudaSuccess) return e;
     const int64_t quads = (nnz + 3) / 4;
     const int64_t n = quads > X.rows ? quads : X.rows;
@@ -313,8 +326,8 @@ k_transpose_fill(Csr X, const int32_t* __restrict__ t_ptr, int32_t* __restrict__
 // ---------------------------------------------------------------------------------------------------
 // Paneled transpose (triple product): rows [row_begin, row_end) of X are cut into panels of `panel_w` rows and the
 // transposes of the panels are stored back to back as ONE CSR with np * X.cols rows -- row p * X.cols + c holds the
-// entries (r, x_rc) of column c with r in panel p.  t_ptr + p * X.cols is then the row-pointer array of panel p's
-// transpose over the shared idx / val arrays.  The triple product accumulates one column panel of C at a time, so
+// entries (r, x_rc) of column c with r in panel p, each stored as the pair (r, c) in t_kc next to its value.
+// t_ptr + p * X.cols is then the row-pointer array of panel p's transpose over the shared t_kc / t_val arrays.  The triple product accumulates one column panel of C at a time, so
 // the slice of H^T it gathers from (a few tens of MB) stays L2 resident.
 template <int LANES>
 __global__ void __launch_bounds__(256)
@@ -330,7 +343,7 @@ k_transpose_count_panels(Csr X, int row_begin, int row_end, int panel_w, int32_t
 template <int LANES>
 __global__ void __launch_bounds__(256)
 k_transpose_fill_panels(Csr X, int row_begin, int row_end, int panel_w, const int32_t* __restrict__ t_ptr,
-                        int32_t* __restrict__ cursor, int32_t* __restrict__ t_idx, double* __restrict__ t_val) {
+                        int32_t* __restrict__ cursor, int2* __restrict__ t_kc, double* __restrict__ t_val) {
     const int r = row_begin + (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const int gl = threadIdx.x % LANES;
     if (r >= row_end) return;
@@ -346,10 +359,10 @@ k_transpose_fill_panels(Csr X, int row_begin, int row_end, int panel_w, const in
         const int b1 = c1 >= 0 ? __ldg(t_ptr + off + c1) : 0;
         const int o0 = atomicAdd(cursor + off + c0, 1);
         const int o1 = c1 >= 0 ? atomicAdd(cursor + off + c1, 1) : 0;
-        t_idx[b0 + o0] = r;
+        t_kc[b0 + o0] = make_int2(r, c0);
         t_val[b0 + o0] = v0;
         if (c1 >= 0) {
-            t_idx[b1 + o1] = r;
+            t_kc[b1 + o1] = make_int2(r, c1);
             t_val[b1 + o1] = v1;
         }
     }
@@ -367,14 +380,14 @@ cudaError_t launch_transpose_count_panels(const LaunchCtx& lc, const Csr& X, int
     return cudaSuccess;
 }
 cudaError_t launch_transpose_fill_panels(const LaunchCtx& lc, const Csr& X, int64_t nnz, int row_begin, int row_end,
-                                         int panel_w, const int32_t* t_ptr, int32_t* d_cursor, int32_t* t_idx,
+                                         int panel_w, const int32_t* t_ptr, int32_t* d_cursor, int2* t_kc,
                                          double* t_val) {
     const int rows = row_end - row_begin;
     if (rows <= 0) return cudaSuccess;
     if (nnz >= (int64_t)48 * X.rows)
-        k_transpose_fill_panels<32><<<(rows + 7) / 8, 256, 0, lc.stream>>>(X, row_begin, row_end, panel_w, t_ptr, d_cursor, t_idx, t_val);
+        k_transpose_fill_panels<32><<<(rows + 7) / 8, 256, 0, lc.stream>>>(X, row_begin, row_end, panel_w, t_ptr, d_cursor, t_kc, t_val);
     else
-        k_transpose_fill_panels<8><<<(rows + 31) / 32, 256, 0, lc.stream>>>(X, row_begin, row_end, panel_w, t_ptr, d_cursor, t_idx, t_val);
+        k_transpose_fill_panels<8><<<(rows + 31) / 32, 256, 0, lc.stream>>>(X, row_begin, row_end, panel_w, t_ptr, d_cursor, t_kc, t_val);
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
 }

@@ -339,7 +339,7 @@ int upload(int rows, int cols, const int32_t* ptr, const int32_t* idx, const dou
     if (nnz > 0 && (!idx || !val)) return fail(SPGEMM_B200_ERR_ARG, "null indices/values with nnz > 0");
     if (rows > 0 && ptr[0] != 0) return fail(SPGEMM_B200_ERR_ARG, "indptr[0] must be 0");
     spgemm_b200_mat* m = new spgemm_b200_mat{rows, cols, nnz, nullptr, nullptr, nullptr, true, g.device,
-                                             nullptr, false, false, false, false, nullptr};
+                                             nullptr, false, false, false, false, false, nullptr};
     int rc;
     if ((rc = dalloc(&m->ptr, (size_t)rows + 1)) || (rc = dalloc(&m->idx, (size_t)nnz)) ||
         (rc = dalloc(&m->val, (size_t)nnz))) {
@@ -380,7 +380,7 @@ int transpose_impl(const spgemm_b200_mat* x, spgemm_b200_mat** out, bool sort_de
     Ctx& g = cx();
     NvtxRange nv("spgemm_b200:transpose");
     spgemm_b200_mat* t = new spgemm_b200_mat{x->cols, x->rows, x->nnz, nullptr, nullptr, nullptr, true, g.device,
-                                             nullptr, false, false, false, false, nullptr};
+                                             nullptr, false, false, false, false, false, nullptr};
     int32_t *counts = nullptr, *cursor = nullptr;
     int64_t* tmp = nullptr;
     int rc;
@@ -412,17 +412,17 @@ int transpose_impl(const spgemm_b200_mat* x, spgemm_b200_mat** out, bool sort_de
 int ensure_checked(spgemm_b200_mat* m1, spgemm_b200_mat* m2) {
     Ctx& g = cx();
     spgemm_b200_mat* ms[2] = {m1, m2 == m1 ? nullptr : m2};
-    int32_t* h = static_cast<int32_t*>(g.h_small) + 64;      // 2 x int32[4] of the pinned staging block
+    int32_t* h = static_cast<int32_t*>(g.h_small) + 64;      // 2 x int32[8] of the pinned staging block
     bool pending = false;
     for (int k = 0; k < 2; ++k) {
         spgemm_b200_mat* m = ms[k];
         if (!m || m->checked) continue;
         if (!m->d_flags) {
-            int rc = dalloc(&m->d_flags, 4);
+            int rc = dalloc(&m->d_flags, 8);
             if (rc) return rc;
         }
         CU(launch_check_csr(lctx(), view(m), m->nnz, m->d_flags));
-        CU(cudaMemcpyAsync(h + 4 * k, m->d_flags, 16, cudaMemcpyDeviceToHost, g.stream));
+        CU(cudaMemcpyAsync(h + 8 * k, m->d_flags, 32, cudaMemcpyDeviceToHost, g.stream));
         pending = true;
     }
     if (!pending) {
@@ -435,8 +435,9 @@ int ensure_checked(spgemm_b200_mat* m1, spgemm_b200_mat* m2) {
         spgemm_b200_mat* m = ms[k];
         if (!m || m->checked) continue;
         m->checked = true;
-        m->sorted = h[4 * k] != 0;
-        m->valid = h[4 * k + 3] == 0;
+        m->sorted = h[8 * k] != 0;
+        m->valid = h[8 * k + 3] == 0;
+        m->runs = m->sorted && h[8 * k + 4] == h[8 * k + 5];
     }
     for (int k = 0; k < 2; ++k)
         if (ms[k] && !ms[k]->valid)
@@ -454,10 +455,10 @@ int sorted_view(spgemm_b200_mat* m, spgemm_b200_mat** out) {
     if (!m->owns) {                                           // borrowed arrays are never modified: sort a copy
         if (m->shadow) { *out = m->shadow; return SPGEMM_B200_OK; }
         t = new spgemm_b200_mat{m->rows, m->cols, m->nnz, nullptr, nullptr, nullptr, true, g.device,
-                                nullptr, false, false, false, false, nullptr};
+                                nullptr, false, false, false, false, false, nullptr};
         int rc;
         if ((rc = dalloc(&t->ptr, (size_t)m->rows + 1)) || (rc = dalloc(&t->idx, (size_t)m->nnz)) ||
-            (rc = dalloc(&t->val, (size_t)m->nnz)) || (rc = dalloc(&t->d_flags, 4))) {
+            (rc = dalloc(&t->val, (size_t)m->nnz)) || (rc = dalloc(&t->d_flags, 8))) {
             mat_release(t);
             return rc;
         }
@@ -663,11 +664,12 @@ int dense_rows(spgemm_b200_mat* a, spgemm_b200_mat* b_in, int upper_only, int r0
 
 // Paneled transpose of rows [plan.k0, n) of H (analysis.cu): one CSR with plan.np * H.cols rows.
 struct PanelT {
-    int32_t *ptr = nullptr, *idx = nullptr;
+    int32_t* ptr = nullptr;
+    int2* kc = nullptr;            // (row of H, column of H) of every entry
     double* val = nullptr;
 };
 static void panels_release(PanelT& t) {
-    dfree(t.ptr); dfree(t.idx); dfree(t.val);
+    dfree(t.ptr); dfree(t.kc); dfree(t.val);
     t = PanelT();
 }
 static int transpose_panels(const spgemm_b200_mat* h, const TriplePlan& plan, PanelT* out) {
@@ -679,7 +681,7 @@ static int transpose_panels(const spgemm_b200_mat* h, const TriplePlan& plan, Pa
     int32_t *counts = nullptr, *cursor = nullptr;
     int64_t* tmp = nullptr;
     int rc;
-    if ((rc = dalloc(&t.ptr, trows + 1)) || (rc = dalloc(&t.idx, (size_t)h->nnz)) || (rc = dalloc(&t.val, (size_t)h->nnz)) ||
+    if ((rc = dalloc(&t.ptr, trows + 1)) || (rc = dalloc(&t.kc, (size_t)h->nnz)) || (rc = dalloc(&t.val, (size_t)h->nnz)) ||
         (rc = dalloc(&counts, trows + 1)) || (rc = dalloc(&cursor, trows + 1)) || (rc = dalloc(&tmp, 1032))) {
         panels_release(t); dfree(counts); dfree(cursor); dfree(tmp);
         return rc;
@@ -690,7 +692,7 @@ static int transpose_panels(const spgemm_b200_mat* h, const TriplePlan& plan, Pa
     if (e == cudaSuccess) e = launch_transpose_count_panels(lc, view(h), h->nnz, plan.k0, h->rows, plan.panel_w, counts);
     if (e == cudaSuccess) e = launch_scan_i32(lc, counts, t.ptr, (int)trows, tmp);
     if (e == cudaSuccess)
-        e = launch_transpose_fill_panels(lc, view(h), h->nnz, plan.k0, h->rows, plan.panel_w, t.ptr, cursor, t.idx, t.val);
+        e = launch_transpose_fill_panels(lc, view(h), h->nnz, plan.k0, h->rows, plan.panel_w, t.ptr, cursor, t.kc, t.val);
     dfree(counts); dfree(cursor); dfree(tmp);
     if (e != cudaSuccess) {
         panels_release(t);
@@ -719,14 +721,16 @@ int triple_rows(const spgemm_b200_mat* h, const spgemm_b200_mat* q, const spgemm
         e = launch_triple_red(lctx(), view(h), view(q), view(ht), ht->desc_sorted, upper_only != 0, r0, r1 - r0, d_c, d_cnt);
         mat_release(own);
     } else {
+        // (a caller-supplied plain transpose `ht` is only used by the round-1 kernel: the panels store (row, column)
+        //  pairs, which a CSR transpose does not have)
         TriplePlan plan = triple_plan(h->rows, r0, upper_only != 0, h->nnz, h->cols);
         PanelT t;
-        const bool borrow = ht && plan.np == 1;               // one panel: a plain transpose serves as it is
-        if (!borrow && (rc = transpose_panels(h, plan, &t))) return rc;
+        if ((rc = transpose_panels(h, plan, &t))) return rc;
         mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
         NvtxRange nv("spgemm_b200:triple");
-        e = launch_triple_panels(lctx(), view(h), view(q), borrow ? ht->ptr : t.ptr, borrow ? ht->idx : t.idx,
-                                 borrow ? ht->val : t.val, plan, upper_only != 0, r0, r1 - r0, d_c, d_cnt);
+        const bool q_runs = q->checked && q->runs && env_mode("SPGEMM_B200_TRIPLE_GENERIC") == 0;
+        e = launch_triple_panels(lctx(), view(h), view(q), q_runs, t.ptr, t.kc, t.val, plan, upper_only != 0, r0, r1 - r0,
+                                 d_c, d_cnt);
         panels_release(t);
     }
     if (e != cudaSuccess) return fail(SPGEMM_B200_ERR_CUDA, "triple kernel", e);
@@ -878,7 +882,7 @@ int spgemm_b200_mat_wrap(int rows, int cols, int64_t nnz, const int32_t* d_indpt
     if (!out || !d_indptr || rows < 0 || cols < 0 || nnz < 0) return fail(SPGEMM_B200_ERR_ARG, "mat_wrap: bad argument");
     ENTER_DEFAULT();
     *out = new spgemm_b200_mat{rows, cols, nnz, const_cast<int32_t*>(d_indptr), const_cast<int32_t*>(d_indices),
-                               const_cast<double*>(d_values), false, cx().device, nullptr, false, false, false, false, nullptr};
+                               const_cast<double*>(d_values), false, cx().device, nullptr, false, false, false, false, false, nullptr};
     return SPGEMM_B200_OK;
 }
 

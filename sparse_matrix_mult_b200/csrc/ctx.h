@@ -21,9 +21,10 @@ struct spgemm_b200_mat {
     double* val;
     bool owns;
     int device;                // ordinal of the device the arrays live on
-    int32_t* d_flags;          // device int32[4]: [0] rows sorted ascending (read by the kernels), [1..3] check scratch
-    bool checked;              // the validation pass ran and its verdict is in `sorted` / `valid`
+    int32_t* d_flags;          // device int32[8]: [0] rows sorted ascending (read by the kernels), [1..5] check scratch
+    bool checked;              // the validation pass ran and its verdict is in `sorted` / `valid` / `runs`
     bool sorted, valid;
+    bool runs;                 // every row is one run of consecutive ascending columns (banded matrix)
     bool desc_sorted;          // rows sorted by DESCENDING column (set by the transpose)
     spgemm_b200_mat* shadow;   // row-sorted copy of a borrowed (owns == false) unsorted matrix, built on demand
 };

@@ -39,8 +39,9 @@ cudaError_t launch_row_products(const LaunchCtx& lc, const Csr& A, const Csr& B,
                                 bool upper_only, int64_t* d_prod, int32_t* d_nnz, int32_t* d_lists,
                                 int32_t* d_cursor, unsigned long long* d_total);
 
-// d_flags (device int32[4]): [0] = 1 when every row of X has non-decreasing column indices, [3] = number of
-// invalid entries (column out of range, indptr not monotone / not ending at nnz); [1], [2] scratch.
+// d_flags (device int32[8]): [0] = 1 when every row of X has non-decreasing column indices, [3] = number of
+// invalid entries (column out of range, indptr not monotone / not ending at nnz); [4] == [5] when every row is one
+// run of consecutive columns; [1], [2] scratch.
 cudaError_t launch_check_csr(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_flags);
 
 // out[0] = 0, out[i+1] = out[i] + in[i]  (in int32[n], out OutT[n+1]); d_tmp holds >= 1025 int64.
@@ -62,7 +63,7 @@ cudaError_t launch_transpose_fill(const LaunchCtx& lc, const Csr& X, int64_t nnz
 cudaError_t launch_transpose_count_panels(const LaunchCtx& lc, const Csr& X, int64_t nnz, int row_begin, int row_end,
                                           int panel_w, int32_t* d_counts);
 cudaError_t launch_transpose_fill_panels(const LaunchCtx& lc, const Csr& X, int64_t nnz, int row_begin, int row_end,
-                                         int panel_w, const int32_t* t_ptr, int32_t* d_cursor, int32_t* t_idx,
+                                         int panel_w, const int32_t* t_ptr, int32_t* d_cursor, int2* t_kc,
                                          double* t_val);
 
 // rows sorted by column (ascending or descending), in place, any row length; d_long_list: int32[rows + 1] scratch
@@ -105,9 +106,10 @@ struct TriplePlan {
     int k0, np, panel_w;
 };
 TriplePlan triple_plan(int n, int row_begin, bool upper_only, int64_t h_nnz, int h_cols);
-// t_ptr / t_idx / t_val: paneled transpose of rows [plan.k0, n) of H (launch_transpose_*_panels)
-cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q, const int32_t* t_ptr,
-                                 const int32_t* t_idx, const double* t_val, const TriplePlan& plan, bool upper_only,
+// t_ptr / t_kc / t_val: paneled transpose of rows [plan.k0, n) of H (launch_transpose_*_panels); q_runs: every row
+// of Q is one run of consecutive, ascending columns (banded Q), which selects the lean kernel
+cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q, bool q_runs, const int32_t* t_ptr,
+                                 const int2* t_kc, const double* t_val, const TriplePlan& plan, bool upper_only,
                                  int row_begin, int nrows, double* d_c,
                                  unsigned long long* d_counters /* [4], zeroed: P1, P2, ticket, spare */);
 // round-1 kernel on the plain transpose Ht (ht_desc: its rows are sorted by descending column)

@@ -98,7 +98,7 @@ struct StepB { int hs, he; double w; };          // hs == he: nothing to contrac
 
 template <bool UPPER>
 __global__ void __launch_bounds__(1024, 1)
-k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int32_t* __restrict__ t_idx,
+k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __restrict__ t_kc,
                 const double* __restrict__ t_val, TriplePlan plan, int row_begin, int nrows, int win_cap,
                 double* __restrict__ C, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -240,7 +240,7 @@ k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int32_t* 
                                 if (pp < L) {
                                     addr[u] = (int)pp + s_d[owner];
                                     wv[u] = s_w[owner];
-                                    k[u] = __ldg(t_idx + addr[u]);
+                                    k[u] = __ldg(t_kc + addr[u]).x;
                                 }
                             }
                         }
@@ -276,6 +276,157 @@ k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int32_t* 
         const int tail = head + 2 * pairs;
         if (tail < count && tid == nt - 1) { st_stream_f64(dst + tail, acc[tail]); acc[tail] = 0.0; }
         // (the ticket barriers at the top of the loop order the clearing before the next item's adds)
+    }
+    triple_flush_counters(p1, p2_total, S.cnt, counters);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Lean kernel for a Q whose every row is ONE RUN of consecutive ascending columns (a banded covariance -- the
+// matrix the triple product is made for; detected by the validation pass, k_check_csr).  Same panels, same
+// (panel, row) items and shared-memory segments as k_triple_panels; the difference is the contraction:
+//   * the products of one entry h_ij of H are w_t = h_ij * q_{j, c0 + t}, t = 0..len-1, for consecutive columns
+//     c0.. of H^T, whose rows are ADJACENT in the panel's CSR: their entries are the one contiguous range
+//     [t_ptr[c0], t_ptr[c0 + len]);
+//   * a warp takes one entry of H at a time: it puts the (up to 64) weights into its table in shared memory and
+//     streams the range with coalesced 128-byte loads of (k, c) pairs and values; entry (k, c, h_kc) adds
+//     w[c - c0] * h_kc into the segment -- the weight is looked up by the column stored WITH the entry, so there is
+//     no per-product bookkeeping at all (k_triple_panels spends ~100 instructions per 32 entries on finding owners);
+//   * the metadata of all entries of H[i,:] (j, h_ij, extent of row j of Q, c0) is loaded by one thread per entry
+//     at the start of the item, so its three dependent gathers are paid once per item, not once per entry, and
+//     the weights of a warp's NEXT entry are in flight while it streams the current one.
+// Dynamic shared memory: acc[win_cap] | hv[nt] | wt[nwarp * 64] | qs[nt] | len[nt] | c0[nt].
+__host__ __device__ inline size_t triple_runs_smem(int win_cap, int threads) {
+    return (size_t)win_cap * 8 + (size_t)threads * 36 + 16;
+}
+
+template <bool UPPER>
+__global__ void __launch_bounds__(1024, 1)
+k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __restrict__ t_kc,
+              const double* __restrict__ t_val, TriplePlan plan, int row_begin, int nrows, int win_cap,
+              double* __restrict__ C, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ TripleScratch S;
+    const int n = H.rows;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+    double* acc = reinterpret_cast<double*>(s_raw);
+    double* s_hv = acc + win_cap;
+    double* s_wt = s_hv + nt + warp * 64;                           // this warp's 64 weights
+    int* s_qs = reinterpret_cast<int*>(s_hv + 3 * nt);              // nwarp * 64 == 2 * nt
+    int* s_len = s_qs + nt;
+    int* s_c0 = s_len + nt;
+    if (tid < 2) S.cnt[tid] = 0;
+    for (int t = tid; t < win_cap; t += nt) acc[t] = 0.0;
+    __syncthreads();
+    unsigned long long p1 = 0, p2_total = 0;
+    while (true) {
+        if (tid == 0) S.item = (int)atomicAdd(counters + 2, 1ULL);
+        __syncthreads();
+        int item = S.item;
+        __syncthreads();
+        int p = 0, rows_p = 0;
+        for (; p < plan.np; ++p) {
+            const int p_end = min(n, plan.k0 + (p + 1) * plan.panel_w);
+            rows_p = UPPER ? max(0, min(nrows, p_end - row_begin)) : nrows;
+            if (item < rows_p) break;
+            item -= rows_p;
+        }
+        if (p >= plan.np) break;
+        const int r = item, i = row_begin + r;
+        const int p0 = plan.k0 + p * plan.panel_w, p1c = min(n, p0 + plan.panel_w);
+        const int lo = UPPER ? max(i, p0) : p0;
+        const bool first_panel = UPPER ? (i >= p0) : (p == 0);
+        double* row = C + (size_t)r * n;
+        const int32_t* hp = t_ptr + (size_t)p * H.cols;
+        const int h_begin = __ldg(H.ptr + i), h_end = __ldg(H.ptr + i + 1);
+        if (first_panel) triple_stream_out(row, nullptr, UPPER ? lo : plan.k0);
+        unsigned p2 = 0;
+        for (int base = h_begin; base < h_end; base += nt) {
+            const int cnt = min(nt, h_end - base);
+            if (tid < cnt) {                               // one thread per entry of H: its metadata, gathered once
+                const int j = __ldg(H.idx + base + tid);
+                const int qs = __ldg(Q.ptr + j);
+                const int len = __ldg(Q.ptr + j + 1) - qs;
+                s_hv[tid] = __ldg(H.val + base + tid);
+                s_qs[tid] = qs;
+                s_len[tid] = len;
+                s_c0[tid] = len > 0 ? __ldg(Q.idx + qs) : 0;
+                if (first_panel) p1 += (unsigned)len;
+            }
+            __syncthreads();
+            // weights of this warp's first entry (first 64 columns of its run)
+            int e = warp;
+            double nw0 = 0.0, nw1 = 0.0;
+            if (e < cnt) {
+                const int len = s_len[e], qs = s_qs[e];
+                const double hv = s_hv[e];
+                if (lane < len) nw0 = hv * __ldcs(Q.val + qs + lane);
+                if (lane + 32 < len) nw1 = hv * __ldcs(Q.val + qs + lane + 32);
+            }
+            for (; e < cnt; e += nwarp) {
+                const int len = s_len[e], qs = s_qs[e], c0 = s_c0[e];
+                const double hv = s_hv[e];
+                for (int t0 = 0; t0 < len; t0 += 64) {
+                    const int cn = min(64, len - t0);
+                    double w0, w1;
+                    if (t0 == 0) { w0 = nw0; w1 = nw1; }
+                    else {
+                        w0 = lane < cn ? hv * __ldcs(Q.val + qs + t0 + lane) : 0.0;
+                        w1 = lane + 32 < cn ? hv * __ldcs(Q.val + qs + t0 + lane + 32) : 0.0;
+                    }
+                    const int cb = c0 + t0;
+                    const int es = __ldg(hp + cb), ee = __ldg(hp + cb + cn);
+                    s_wt[lane] = w0;
+                    s_wt[lane + 32] = w1;
+                    if (t0 + 64 >= len) {                  // last piece of this run: prefetch the next entry's weights
+                        const int en = e + nwarp;
+                        nw0 = 0.0; nw1 = 0.0;
+                        if (en < cnt) {
+                            const int nlen = s_len[en], nqs = s_qs[en];
+                            const double nhv = s_hv[en];
+                            if (lane < nlen) nw0 = nhv * __ldcs(Q.val + nqs + lane);
+                            if (lane + 32 < nlen) nw1 = nhv * __ldcs(Q.val + nqs + lane + 32);
+                        }
+                    }
+                    __syncwarp();
+                    for (int x0 = es; x0 < ee; x0 += 128) {
+                        int2 kc[4];
+                        double v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int x = x0 + 32 * u + lane;
+                            kc[u] = x < ee ? __ldg(t_kc + x) : make_int2(-1, 0);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) v[u] = kc[u].x >= lo ? __ldg(t_val + x0 + 32 * u + lane) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (kc[u].x >= lo) {
+                                atomicAdd(acc + (kc[u].x - lo), s_wt[kc[u].y - cb] * v[u]);
+                                ++p2;
+                            }
+                        }
+                    }
+                    __syncwarp();                          // the table is rewritten by the next piece
+                }
+            }
+            __syncthreads();                               // tables are rewritten by the next slice / item
+        }
+        p2_total += p2;
+        const int count = p1c - lo;
+        double* dst = row + lo;
+        const int head = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1);
+        if (head && tid == 0 && count > 0) { st_stream_f64(dst, acc[0]); acc[0] = 0.0; }
+        const int pairs = (count - head) >> 1;
+        double* d2 = dst + head;
+        double* s2 = acc + head;
+        for (int t = tid; t < pairs; t += nt) {
+            st_stream_f64x2(d2 + 2 * t, s2[2 * t], s2[2 * t + 1]);
+            s2[2 * t] = 0.0;
+            s2[2 * t + 1] = 0.0;
+        }
+        const int tail = head + 2 * pairs;
+        if (tail < count && tid == nt - 1) { st_stream_f64(dst + tail, acc[tail]); acc[tail] = 0.0; }
     }
     triple_flush_counters(p1, p2_total, S.cnt, counters);
 }
@@ -338,7 +489,11 @@ cudaError_t triple_kernels_configure() {
     const int dyn = (int)(g_triple_smem_optin - sizeof(TripleScratch) - 64);
     e = cudaFuncSetAttribute(k_triple_panels<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_triple_panels<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    e = cudaFuncSetAttribute(k_triple_panels<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_triple_runs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_triple_runs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -347,7 +502,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 static int triple_cap_max() {
-    return (int)(((g_triple_smem_optin - sizeof(TripleScratch) - 64 - triple_window_smem(0, 1024)) / 8) & ~(size_t)1);
+    return (int)(((g_triple_smem_optin - sizeof(TripleScratch) - 64 - triple_runs_smem(0, 1024)) / 8) & ~(size_t)1);
 }
 
 // Panels of C for rows [row_begin, ...): as few as the shared-memory accumulator allows (a panel is one segment), more
@@ -359,7 +514,7 @@ TriplePlan triple_plan(int n, int row_begin, bool upper_only, int64_t h_nnz, int
     const int cover = n - plan.k0 > 0 ? n - plan.k0 : 1;
     const int cap = triple_cap_max();
     int np = (cover + cap - 1) / cap;
-    const double covered_bytes = 12.0 * (double)h_nnz * (double)cover / (double)(n > 0 ? n : 1);
+    const double covered_bytes = 16.0 * (double)h_nnz * (double)cover / (double)(n > 0 ? n : 1);
     const double budget = 1.0e6 * env_int("SPGEMM_B200_TRIPLE_L2_MB", 40) - 4.0 * (double)h_cols;
     if (budget > 0) {
         const int np_l2 = (int)(covered_bytes / budget) + 1;
@@ -376,17 +531,18 @@ TriplePlan triple_plan(int n, int row_begin, bool upper_only, int64_t h_nnz, int
     return plan;
 }
 
-cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q, const int32_t* t_ptr,
-                                 const int32_t* t_idx, const double* t_val, const TriplePlan& plan, bool upper_only,
+cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q, bool q_runs, const int32_t* t_ptr,
+                                 const int2* t_kc, const double* t_val, const TriplePlan& plan, bool upper_only,
                                  int row_begin, int nrows, double* d_c, unsigned long long* d_counters) {
     const int n = H.rows;
     if (nrows <= 0 || n <= 0) return cudaSuccess;
     const size_t fixed = sizeof(TripleScratch) + 1024;                    // static scratch + per-block reserve
     const int win = plan.panel_w;
     // 1, 2 or 4 blocks per SM of 1024 / 512 / 256 threads (32 warps per SM at <= 64 registers)
+    auto smem_of = [&](int threads) { return q_runs ? triple_runs_smem(win, threads) : triple_window_smem(win, threads); };
     int per_sm = 1;
     for (int cand : {4, 2}) {
-        if (g_triple_smem_sm / (triple_window_smem(win, 1024 / cand) + fixed) >= (size_t)cand) { per_sm = cand; break; }
+        if (g_triple_smem_sm / (smem_of(1024 / cand) + fixed) >= (size_t)cand) { per_sm = cand; break; }
     }
     const int threads = 1024 / per_sm;
     int64_t items = 0;
@@ -399,11 +555,18 @@ cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q
     int grid = lc.sm_count * per_sm;
     if ((int64_t)grid > items) grid = (int)items;
     if (grid < 1) grid = 1;
-    const size_t smem = triple_window_smem(win, threads);
-    if (upper_only)
-        k_triple_panels<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_idx, t_val, plan, row_begin, nrows, win, d_c, d_counters);
-    else
-        k_triple_panels<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_idx, t_val, plan, row_begin, nrows, win, d_c, d_counters);
+    const size_t smem = smem_of(threads);
+    if (q_runs) {
+        if (upper_only)
+            k_triple_runs<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
+        else
+            k_triple_runs<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
+    } else {
+        if (upper_only)
+            k_triple_panels<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
+        else
+            k_triple_panels<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
+    }
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
 }
