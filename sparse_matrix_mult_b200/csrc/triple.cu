@@ -299,6 +299,29 @@ __host__ __device__ inline size_t triple_runs_smem(int win_cap, int threads) {
     return (size_t)win_cap * 8 + (size_t)threads * 36 + 16;
 }
 
+// Loads of the panel of H^T carry an L2 evict_last policy: the panel (a few tens of MB) is what every block gathers
+// from for the whole pass and should survive the streams of Q and C that pass through L2 beside it.
+__device__ __forceinline__ unsigned long long l2_keep_policy() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ int ld_keep_i32(const int32_t* p, unsigned long long pol) {
+    int v;
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int2 ld_keep_i2(const int2* p, unsigned long long pol) {
+    int2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ld_keep_f64(const double* p, unsigned long long pol) {
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 template <bool UPPER>
 __global__ void __launch_bounds__(1024, 1)
 k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __restrict__ t_kc,
@@ -315,6 +338,7 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
     int* s_qs = reinterpret_cast<int*>(s_hv + 3 * nt);              // nwarp * 64 == 2 * nt
     int* s_len = s_qs + nt;
     int* s_c0 = s_len + nt;
+    const unsigned long long keep = l2_keep_policy();
     if (tid < 2) S.cnt[tid] = 0;
     for (int t = tid; t < win_cap; t += nt) acc[t] = 0.0;
     __syncthreads();
@@ -354,56 +378,76 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
                 if (first_panel) p1 += (unsigned)len;
             }
             __syncthreads();
-            // weights of this warp's first entry (first 64 columns of its run)
+            // Software pipeline over this warp's entries of H: while the range of entry e is streamed, the raw
+            // values q_{j,c} of entry e + nwarp and the bounds of its range of H^T are already in flight.
+            const bool filtered = UPPER && lo > p0;        // the panel holds the diagonal: entries k < i are skipped
             int e = warp;
-            double nw0 = 0.0, nw1 = 0.0;
-            if (e < cnt) {
-                const int len = s_len[e], qs = s_qs[e];
-                const double hv = s_hv[e];
-                if (lane < len) nw0 = hv * __ldcs(Q.val + qs + lane);
-                if (lane + 32 < len) nw1 = hv * __ldcs(Q.val + qs + lane + 32);
-            }
+            double nq0 = 0.0, nq1 = 0.0;
+            int nes = 0, nee = 0;
+            auto prefetch = [&](int en) {
+                nq0 = 0.0; nq1 = 0.0; nes = 0; nee = 0;
+                if (en < cnt) {
+                    const int nlen = s_len[en], nqs = s_qs[en], nc0 = s_c0[en];
+                    if (lane < nlen) nq0 = __ldcs(Q.val + nqs + lane);
+                    if (lane + 32 < nlen) nq1 = __ldcs(Q.val + nqs + lane + 32);
+                    if (nlen > 0) {
+                        nes = ld_keep_i32(hp + nc0, keep);
+                        nee = ld_keep_i32(hp + nc0 + min(64, nlen), keep);
+                    }
+                }
+            };
+            prefetch(e);
             for (; e < cnt; e += nwarp) {
                 const int len = s_len[e], qs = s_qs[e], c0 = s_c0[e];
                 const double hv = s_hv[e];
                 for (int t0 = 0; t0 < len; t0 += 64) {
                     const int cn = min(64, len - t0);
-                    double w0, w1;
-                    if (t0 == 0) { w0 = nw0; w1 = nw1; }
-                    else {
-                        w0 = lane < cn ? hv * __ldcs(Q.val + qs + t0 + lane) : 0.0;
-                        w1 = lane + 32 < cn ? hv * __ldcs(Q.val + qs + t0 + lane + 32) : 0.0;
-                    }
                     const int cb = c0 + t0;
-                    const int es = __ldg(hp + cb), ee = __ldg(hp + cb + cn);
-                    s_wt[lane] = w0;
-                    s_wt[lane + 32] = w1;
-                    if (t0 + 64 >= len) {                  // last piece of this run: prefetch the next entry's weights
-                        const int en = e + nwarp;
-                        nw0 = 0.0; nw1 = 0.0;
-                        if (en < cnt) {
-                            const int nlen = s_len[en], nqs = s_qs[en];
-                            const double nhv = s_hv[en];
-                            if (lane < nlen) nw0 = nhv * __ldcs(Q.val + nqs + lane);
-                            if (lane + 32 < nlen) nw1 = nhv * __ldcs(Q.val + nqs + lane + 32);
-                        }
+                    double q0, q1;
+                    int es, ee;
+                    if (t0 == 0) { q0 = nq0; q1 = nq1; es = nes; ee = nee; }
+                    else {
+                        q0 = lane < cn ? __ldcs(Q.val + qs + t0 + lane) : 0.0;
+                        q1 = lane + 32 < cn ? __ldcs(Q.val + qs + t0 + lane + 32) : 0.0;
+                        es = ld_keep_i32(hp + cb, keep);
+                        ee = ld_keep_i32(hp + cb + cn, keep);
                     }
+                    if (t0 + 64 >= len) prefetch(e + nwarp);   // last piece of this run: start the next entry's loads
+                    s_wt[lane] = hv * q0;
+                    s_wt[lane + 32] = hv * q1;
                     __syncwarp();
-                    for (int x0 = es; x0 < ee; x0 += 128) {
-                        int2 kc[4];
-                        double v[4];
+                    const double* wt = s_wt - cb;              // weight of column c: wt[c]
+                    int x0 = es + lane;
+                    if (!filtered) {
+                        // every entry of the range contributes: (k, c) pairs and values are loaded together
+                        for (; x0 + 96 < ee; x0 += 128) {      // four full 32-entry steps: no bounds checks
+                            int2 kc[4];
+                            double v[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int x = x0 + 32 * u + lane;
-                            kc[u] = x < ee ? __ldg(t_kc + x) : make_int2(-1, 0);
+                            for (int u = 0; u < 4; ++u) { kc[u] = ld_keep_i2(t_kc + x0 + 32 * u, keep); v[u] = ld_keep_f64(t_val + x0 + 32 * u, keep); }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) atomicAdd(acc + (kc[u].x - lo), wt[kc[u].y] * v[u]);
                         }
+                        for (; x0 < ee; x0 += 32) {
+                            const int2 kc = ld_keep_i2(t_kc + x0, keep);
+                            const double v = ld_keep_f64(t_val + x0, keep);
+                            atomicAdd(acc + (kc.x - lo), wt[kc.y] * v);
+                        }
+                        if (lane == 0) p2 += (unsigned)(ee - es);
+                    } else {
+                        for (; x0 - lane < ee; x0 += 128) {
+                            int2 kc[4];
+                            double v[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) v[u] = kc[u].x >= lo ? __ldg(t_val + x0 + 32 * u + lane) : 0.0;
+                            for (int u = 0; u < 4; ++u) kc[u] = x0 + 32 * u < ee ? ld_keep_i2(t_kc + x0 + 32 * u, keep) : make_int2(-1, 0);
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (kc[u].x >= lo) {
-                                atomicAdd(acc + (kc[u].x - lo), s_wt[kc[u].y - cb] * v[u]);
-                                ++p2;
+                            for (int u = 0; u < 4; ++u) v[u] = kc[u].x >= lo ? ld_keep_f64(t_val + x0 + 32 * u, keep) : 0.0;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const bool hit = kc[u].x >= lo;
+                                if (hit) atomicAdd(acc + (kc[u].x - lo), wt[kc[u].y] * v[u]);
+                                const unsigned m = __ballot_sync(FULL, hit);
+                                if (lane == 0) p2 += __popc(m);
                             }
                         }
                     }
