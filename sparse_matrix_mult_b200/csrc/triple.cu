@@ -287,16 +287,17 @@ k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __r
 //   * the products of one entry h_ij of H are w_t = h_ij * q_{j, c0 + t}, t = 0..len-1, for consecutive columns
 //     c0.. of H^T, whose rows are ADJACENT in the panel's CSR: their entries are the one contiguous range
 //     [t_ptr[c0], t_ptr[c0 + len]);
-//   * a warp takes one entry of H at a time: it puts the (up to 64) weights into its table in shared memory and
+//   * a warp takes one entry of H at a time: it puts the (up to 96) weights into its table in shared memory and
 //     streams the range with coalesced 128-byte loads of (k, c) pairs and values; entry (k, c, h_kc) adds
 //     w[c - c0] * h_kc into the segment -- the weight is looked up by the column stored WITH the entry, so there is
 //     no per-product bookkeeping at all (k_triple_panels spends ~100 instructions per 32 entries on finding owners);
 //   * the metadata of all entries of H[i,:] (j, h_ij, extent of row j of Q, c0) is loaded by one thread per entry
 //     at the start of the item, so its three dependent gathers are paid once per item, not once per entry, and
 //     the weights of a warp's NEXT entry are in flight while it streams the current one.
-// Dynamic shared memory: acc[win_cap] | hv[nt] | wt[nwarp * 64] | qs[nt] | len[nt] | c0[nt].
+// Dynamic shared memory: acc[win_cap] | hv[nt] | wt[nwarp * 96] | qs[nt] | len[nt] | c0[nt].
+constexpr int kRunPiece = 96;                    // columns of a run handled per pass of the weight table
 __host__ __device__ inline size_t triple_runs_smem(int win_cap, int threads) {
-    return (size_t)win_cap * 8 + (size_t)threads * 36 + 16;
+    return (size_t)win_cap * 8 + (size_t)threads * 44 + 16;
 }
 
 // Loads of the panel of H^T carry an L2 evict_last policy: the panel (a few tens of MB) is what every block gathers
@@ -334,8 +335,8 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
     const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     double* acc = reinterpret_cast<double*>(s_raw);
     double* s_hv = acc + win_cap;
-    double* s_wt = s_hv + nt + warp * 64;                           // this warp's 64 weights
-    int* s_qs = reinterpret_cast<int*>(s_hv + 3 * nt);              // nwarp * 64 == 2 * nt
+    double* s_wt = s_hv + nt + warp * kRunPiece;                    // this warp's 96 weights
+    int* s_qs = reinterpret_cast<int*>(s_hv + 4 * nt);              // nwarp * 96 == 3 * nt
     int* s_len = s_qs + nt;
     int* s_c0 = s_len + nt;
     const unsigned long long keep = l2_keep_policy();
@@ -382,17 +383,18 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
             // values q_{j,c} of entry e + nwarp and the bounds of its range of H^T are already in flight.
             const bool filtered = UPPER && lo > p0;        // the panel holds the diagonal: entries k < i are skipped
             int e = warp;
-            double nq0 = 0.0, nq1 = 0.0;
+            double nq0 = 0.0, nq1 = 0.0, nq2 = 0.0;
             int nes = 0, nee = 0;
             auto prefetch = [&](int en) {
-                nq0 = 0.0; nq1 = 0.0; nes = 0; nee = 0;
+                nq0 = 0.0; nq1 = 0.0; nq2 = 0.0; nes = 0; nee = 0;
                 if (en < cnt) {
                     const int nlen = s_len[en], nqs = s_qs[en], nc0 = s_c0[en];
                     if (lane < nlen) nq0 = __ldcs(Q.val + nqs + lane);
                     if (lane + 32 < nlen) nq1 = __ldcs(Q.val + nqs + lane + 32);
+                    if (lane + 64 < nlen) nq2 = __ldcs(Q.val + nqs + lane + 64);
                     if (nlen > 0) {
                         nes = ld_keep_i32(hp + nc0, keep);
-                        nee = ld_keep_i32(hp + nc0 + min(64, nlen), keep);
+                        nee = ld_keep_i32(hp + nc0 + min(kRunPiece, nlen), keep);
                     }
                 }
             };
@@ -400,57 +402,70 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
             for (; e < cnt; e += nwarp) {
                 const int len = s_len[e], qs = s_qs[e], c0 = s_c0[e];
                 const double hv = s_hv[e];
-                for (int t0 = 0; t0 < len; t0 += 64) {
-                    const int cn = min(64, len - t0);
+                for (int t0 = 0; t0 < len; t0 += kRunPiece) {
+                    const int cn = min(kRunPiece, len - t0);
                     const int cb = c0 + t0;
-                    double q0, q1;
+                    double q0, q1, q2;
                     int es, ee;
-                    if (t0 == 0) { q0 = nq0; q1 = nq1; es = nes; ee = nee; }
+                    if (t0 == 0) { q0 = nq0; q1 = nq1; q2 = nq2; es = nes; ee = nee; }
                     else {
                         q0 = lane < cn ? __ldcs(Q.val + qs + t0 + lane) : 0.0;
                         q1 = lane + 32 < cn ? __ldcs(Q.val + qs + t0 + lane + 32) : 0.0;
+                        q2 = lane + 64 < cn ? __ldcs(Q.val + qs + t0 + lane + 64) : 0.0;
                         es = ld_keep_i32(hp + cb, keep);
                         ee = ld_keep_i32(hp + cb + cn, keep);
                     }
-                    if (t0 + 64 >= len) prefetch(e + nwarp);   // last piece of this run: start the next entry's loads
+                    if (t0 + kRunPiece >= len) prefetch(e + nwarp);   // last piece of this run: start the next entry's loads
                     s_wt[lane] = hv * q0;
                     s_wt[lane + 32] = hv * q1;
+                    s_wt[lane + 64] = hv * q2;
                     __syncwarp();
                     const double* wt = s_wt - cb;              // weight of column c: wt[c]
-                    int x0 = es + lane;
-                    if (!filtered) {
-                        // every entry of the range contributes: (k, c) pairs and values are loaded together
-                        for (; x0 + 96 < ee; x0 += 128) {      // four full 32-entry steps: no bounds checks
-                            int2 kc[4];
-                            double v[4];
+                    // the range [es, ee), 128 entries per step: loads of the four sub-steps in flight together, then the
+                    // four adds as overlapped optimistic compare-and-swaps (the rare loser retries with atomicAdd)
+                    for (int xb = es; xb < ee; xb += 128) {
+                        int2 kc[4];
+                        double v[4];
+                        bool hit[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) { kc[u] = ld_keep_i2(t_kc + x0 + 32 * u, keep); v[u] = ld_keep_f64(t_val + x0 + 32 * u, keep); }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) atomicAdd(acc + (kc[u].x - lo), wt[kc[u].y] * v[u]);
+                        for (int u = 0; u < 4; ++u) {
+                            const int x = xb + 32 * u + lane;
+                            kc[u] = x < ee ? ld_keep_i2(t_kc + x, keep) : make_int2(-1, 0);
+                            if (!filtered) v[u] = x < ee ? ld_keep_f64(t_val + x, keep) : 0.0;
                         }
-                        for (; x0 < ee; x0 += 32) {
-                            const int2 kc = ld_keep_i2(t_kc + x0, keep);
-                            const double v = ld_keep_f64(t_val + x0, keep);
-                            atomicAdd(acc + (kc.x - lo), wt[kc.y] * v);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            hit[u] = kc[u].x >= lo;            // also false for the (-1, 0) filler
+                            if (filtered) v[u] = hit[u] ? ld_keep_f64(t_val + xb + 32 * u + lane, keep) : 0.0;
                         }
-                        if (lane == 0) p2 += (unsigned)(ee - es);
-                    } else {
-                        for (; x0 - lane < ee; x0 += 128) {
-                            int2 kc[4];
-                            double v[4];
+                        unsigned long long* slot[4];
+                        unsigned long long seen[4], got[4];
+                        double add[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) kc[u] = x0 + 32 * u < ee ? ld_keep_i2(t_kc + x0 + 32 * u, keep) : make_int2(-1, 0);
+                        for (int u = 0; u < 4; ++u) {
+                            slot[u] = reinterpret_cast<unsigned long long*>(acc + (hit[u] ? kc[u].x - lo : 0));
+                            add[u] = hit[u] ? wt[kc[u].y] * v[u] : 0.0;
+                            seen[u] = hit[u] ? *slot[u] : 0ULL;
+                        }
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) v[u] = kc[u].x >= lo ? ld_keep_f64(t_val + x0 + 32 * u, keep) : 0.0;
+                        for (int u = 0; u < 4; ++u) {
+                            got[u] = seen[u];
+                            if (hit[u])
+                                got[u] = atomicCAS(slot[u], seen[u],
+                                                   (unsigned long long)__double_as_longlong(__longlong_as_double((long long)seen[u]) + add[u]));
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (got[u] != seen[u]) atomicAdd(reinterpret_cast<double*>(slot[u]), add[u]);
+                        if (filtered) {
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const bool hit = kc[u].x >= lo;
-                                if (hit) atomicAdd(acc + (kc[u].x - lo), wt[kc[u].y] * v[u]);
-                                const unsigned m = __ballot_sync(FULL, hit);
+                                const unsigned m = __ballot_sync(FULL, hit[u]);
                                 if (lane == 0) p2 += __popc(m);
                             }
                         }
                     }
+                    if (!filtered && lane == 0) p2 += (unsigned)(ee - es);
                     __syncwarp();                          // the table is rewritten by the next piece
                 }
             }
