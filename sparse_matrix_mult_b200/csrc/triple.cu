@@ -421,51 +421,23 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
                     s_wt[lane + 64] = hv * q2;
                     __syncwarp();
                     const double* wt = s_wt - cb;              // weight of column c: wt[c]
-                    // the range [es, ee), 128 entries per step: loads of the four sub-steps in flight together, then the
-                    // four adds as overlapped optimistic compare-and-swaps (the rare loser retries with atomicAdd)
-                    for (int xb = es; xb < ee; xb += 128) {
-                        int2 kc[4];
-                        double v[4];
-                        bool hit[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int x = xb + 32 * u + lane;
-                            kc[u] = x < ee ? ld_keep_i2(t_kc + x, keep) : make_int2(-1, 0);
-                            if (!filtered) v[u] = x < ee ? ld_keep_f64(t_val + x, keep) : 0.0;
+                    // the range [es, ee), 32 entries per step, as a rolling pipeline: the (k, c) pairs and values of the
+                    // next step are in flight while the current step is multiplied and added (ranges are ~100-200
+                    // entries long: wider steps would leave most lanes of the last one idle)
+                    int x = es + lane;
+                    int2 kc = x < ee ? ld_keep_i2(t_kc + x, keep) : make_int2(-1, 0);
+                    double v = x < ee ? ld_keep_f64(t_val + x, keep) : 0.0;
+                    for (; x < ee; x += 32) {
+                        const int xn = x + 32;
+                        const int2 kcn = xn < ee ? ld_keep_i2(t_kc + xn, keep) : make_int2(-1, 0);
+                        const double vn = xn < ee ? ld_keep_f64(t_val + xn, keep) : 0.0;
+                        if (!filtered || kc.x >= lo) {
+                            atomicAdd(acc + (kc.x - lo), wt[kc.y] * v);
+                            ++p2;
                         }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            hit[u] = kc[u].x >= lo;            // also false for the (-1, 0) filler
-                            if (filtered) v[u] = hit[u] ? ld_keep_f64(t_val + xb + 32 * u + lane, keep) : 0.0;
-                        }
-                        unsigned long long* slot[4];
-                        unsigned long long seen[4], got[4];
-                        double add[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            slot[u] = reinterpret_cast<unsigned long long*>(acc + (hit[u] ? kc[u].x - lo : 0));
-                            add[u] = hit[u] ? wt[kc[u].y] * v[u] : 0.0;
-                            seen[u] = hit[u] ? *slot[u] : 0ULL;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            got[u] = seen[u];
-                            if (hit[u])
-                                got[u] = atomicCAS(slot[u], seen[u],
-                                                   (unsigned long long)__double_as_longlong(__longlong_as_double((long long)seen[u]) + add[u]));
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (got[u] != seen[u]) atomicAdd(reinterpret_cast<double*>(slot[u]), add[u]);
-                        if (filtered) {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const unsigned m = __ballot_sync(FULL, hit[u]);
-                                if (lane == 0) p2 += __popc(m);
-                            }
-                        }
+                        kc = kcn;
+                        v = vn;
                     }
-                    if (!filtered && lane == 0) p2 += (unsigned)(ee - es);
                     __syncwarp();                          // the table is rewritten by the next piece
                 }
             }
