@@ -253,7 +253,7 @@ cudaError_t launch_scan_i32(const LaunchCtx& lc, const int32_t* in, int32_t* out
 // Numeric binning by exact row nnz (one thread per row, block-aggregated list append).
 __global__ void __launch_bounds__(256)
 k_bin_by_nnz(const int32_t* __restrict__ nnz, int nrows, int32_t* __restrict__ lists,
-             int32_t* __restrict__ cursor, int cap_h4k, int cap_h12k) {
+             int32_t* __restrict__ cursor) {
     __shared__ int s_cnt[NUM_BINS], s_base[NUM_BINS];
     if (threadIdx.x < NUM_BINS) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -265,8 +265,6 @@ k_bin_by_nnz(const int32_t* __restrict__ nnz, int nrows, int32_t* __restrict__ l
             if (c <= kWarpCap64) bin = NUM_W64;
             else if (c <= kWarpCap256) bin = NUM_W256;
             else if (c <= kWarpCap1K) bin = NUM_W1K;
-            else if (c <= cap_h4k) bin = NUM_H4K;
-            else if (c <= cap_h12k) bin = NUM_H12K;
             else bin = NUM_RANK;
         }
     }
@@ -282,9 +280,9 @@ k_bin_by_nnz(const int32_t* __restrict__ nnz, int nrows, int32_t* __restrict__ l
 }
 
 cudaError_t launch_bin_by_nnz(const LaunchCtx& lc, const int32_t* d_nnz, int nrows, int32_t* d_lists,
-                              int32_t* d_cursor, int cap_h4k, int cap_h12k) {
+                              int32_t* d_cursor) {
     if (nrows <= 0) return cudaSuccess;
-    k_bin_by_nnz<<<(nrows + 255) / 256, 256, 0, lc.stream>>>(d_nnz, nrows, d_lists, d_cursor, cap_h4k, cap_h12k);
+    k_bin_by_nnz<<<(nrows + 255) / 256, 256, 0, lc.stream>>>(d_nnz, nrows, d_lists, d_cursor);
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
 }

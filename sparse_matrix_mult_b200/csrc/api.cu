@@ -618,9 +618,7 @@ int csr_impl(spgemm_b200_mat* a, spgemm_b200_mat* b_in, int upper_only, int r0, 
         e = launch_symbolic(lc, job, d_lists, sym_counts, d_nnz, d_work);
         if (e == cudaSuccess) e = launch_scan_i64(lc, d_nnz, res->d_ptr, m, scan_tmp);
         if (e == cudaSuccess) e = cudaMemsetAsync(d_cursor, 0, 16 * sizeof(int32_t), g.stream);
-        int cap_h4k = 0, cap_h12k = 0;
-        numeric_hash_caps(n, &cap_h4k, &cap_h12k);
-        if (e == cudaSuccess) e = launch_bin_by_nnz(lc, d_nnz, m, d_lists, d_cursor, cap_h4k, cap_h12k);
+        if (e == cudaSuccess) e = launch_bin_by_nnz(lc, d_nnz, m, d_lists, d_cursor);
         if (e != cudaSuccess) return bail(fail(SPGEMM_B200_ERR_CUDA, "symbolic phase", e));
         mark(EV_SYMBOLIC);
     }
@@ -706,23 +704,11 @@ static int transpose_panels(const spgemm_b200_mat* h, const TriplePlan& plan, Pa
 int triple_rows(const spgemm_b200_mat* h, const spgemm_b200_mat* q, const spgemm_b200_mat* ht, int upper_only, int r0,
                 int r1, double* d_c, unsigned long long* d_cnt) {
     Ctx& g = cx();
-    const int mode = env_mode("SPGEMM_B200_TRIPLE_MODE");
+    (void)ht;      // a plain CSR transpose cannot stand in for the panels: they store (row, column) pairs
     cudaError_t e = cudaMemsetAsync(d_cnt, 0, 32, g.stream);
     if (e != cudaSuccess) return fail(SPGEMM_B200_ERR_CUDA, "triple counters", e);
     int rc;
-    if (mode == 2) {                                          // round-1 kernel on the plain transpose
-        spgemm_b200_mat* own = nullptr;
-        if (!ht) {
-            if ((rc = transpose_impl(h, &own, true))) return rc;
-            ht = own;
-        }
-        mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
-        NvtxRange nv("spgemm_b200:triple");
-        e = launch_triple_red(lctx(), view(h), view(q), view(ht), ht->desc_sorted, upper_only != 0, r0, r1 - r0, d_c, d_cnt);
-        mat_release(own);
-    } else {
-        // (a caller-supplied plain transpose `ht` is only used by the round-1 kernel: the panels store (row, column)
-        //  pairs, which a CSR transpose does not have)
+    {
         TriplePlan plan = triple_plan(h->rows, r0, upper_only != 0, h->nnz, h->cols);
         PanelT t;
         if ((rc = transpose_panels(h, plan, &t))) return rc;

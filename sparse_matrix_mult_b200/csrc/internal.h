@@ -10,12 +10,10 @@ namespace sb {
 // ---- bins ---------------------------------------------------------------------------------------
 // symbolic bins, by the row's upper bound u = min(P_i, columns left)
 enum { SYM_W64 = 0, SYM_W256, SYM_W1K, SYM_BITMAP, SYM_BINS };
-// numeric bins, by the row's exact nnz: three warp bins, two block-hash bins (4,096 / 12,288 slots), the rank bin
-enum { NUM_W64 = 0, NUM_W256, NUM_W1K, NUM_H4K, NUM_H12K, NUM_RANK, NUM_BINS };
+// numeric bins, by the row's exact nnz
+enum { NUM_W64 = 0, NUM_W256, NUM_W1K, NUM_RANK, NUM_BINS };
 
 constexpr int kWarpCap64 = 48, kWarpCap256 = 192, kWarpCap1K = 768;   // <= 75 % load of the warp tables
-constexpr int kHashSlots4K = 4096, kHashSlots12K = 12288, kHashSlotsWide = 3584;   // wide: beside a 2^20-column table
-constexpr int kHashCap4K = 3072, kHashCap12K = 9216, kHashCapWide = 2688;          // <= 75 % load of the block tables
 
 struct LaunchCtx {
     cudaStream_t stream;
@@ -48,10 +46,9 @@ cudaError_t launch_check_csr(const LaunchCtx& lc, const Csr& X, int64_t nnz, int
 cudaError_t launch_scan_i64(const LaunchCtx& lc, const int32_t* in, int64_t* out, int n, int64_t* d_tmp);
 cudaError_t launch_scan_i32(const LaunchCtx& lc, const int32_t* in, int32_t* out, int n, int64_t* d_tmp);
 
-// numeric binning by exact nnz; cap_h4k / cap_h12k: largest row of the block-hash bins (0 disables a bin: its rows
-// go to the next one), see numeric_hash_caps
+// numeric binning by exact nnz
 cudaError_t launch_bin_by_nnz(const LaunchCtx& lc, const int32_t* d_nnz, int nrows, int32_t* d_lists,
-                              int32_t* d_cursor, int cap_h4k, int cap_h12k);
+                              int32_t* d_cursor);
 
 // CSR transpose: counts -> scan -> fill.  Rows of the transpose come out in arbitrary order.
 cudaError_t launch_transpose_count(const LaunchCtx& lc, const Csr& X, int64_t nnz, int32_t* d_counts);
@@ -88,9 +85,6 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
                            const int32_t* h_counts /* host, NUM_BINS */, const int64_t* c_ptr, int32_t* c_idx,
                            double* c_val, int32_t* d_work_counter);
 cudaError_t sparse_kernels_configure();
-// which block-hash bins the numeric phase can run for a result with `cols` columns (their rank table must fit
-// shared memory beside the hash table)
-void numeric_hash_caps(int cols, int* cap_h4k, int* cap_h12k);
 
 // ---- spgemm_dense.cu ----------------------------------------------------------------------------
 // mode: 0 = choose by products per output element, 1 = shared-memory tiles, 2 = block per row with L2 reductions
@@ -112,9 +106,6 @@ cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q
                                  const int2* t_kc, const double* t_val, const TriplePlan& plan, bool upper_only,
                                  int row_begin, int nrows, double* d_c,
                                  unsigned long long* d_counters /* [4], zeroed: P1, P2, ticket, spare */);
-// round-1 kernel on the plain transpose Ht (ht_desc: its rows are sorted by descending column)
-cudaError_t launch_triple_red(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool ht_desc,
-                              bool upper_only, int row_begin, int nrows, double* d_c, unsigned long long* d_counters);
 cudaError_t triple_kernels_configure();
 
 }  // namespace sb

@@ -6,11 +6,8 @@
 // thread block, chosen by the row's cost bin:
 //   warp bins : open-addressing hash table in shared memory (64 / 256 / 1024 slots per warp), compacted and
 //               bitonic-sorted by column inside the warp
-//   hash bins : (rows of 769..9,216 entries) block-wide hash table of (column, value) in shared memory, filled in ONE
-//               traversal of the products; a column bitmap marked on first insertion gives every key its rank in
-//               the sorted row, so the table is scattered straight to its final place (no sort, no reductions)
-//   rank bin  : (longer rows) occupancy bitmap of the row in shared memory; a popcount prefix over it gives every
-//               column its rank in the sorted row, so values are accumulated in place in C with L2 reductions
+//   block bin : occupancy bitmap of the row in shared memory; a popcount prefix over it gives every column its
+//               rank in the sorted row, so values are accumulated in place in C (no hash table, no sort)
 // Output rows are written at their final position (int64 offsets from the scan of the symbolic counts):
 // no stitch pass.  Entries whose value cancels to zero stay (they are structural in the reference too).
 #include <cstdlib>
@@ -215,8 +212,10 @@ k_numeric_warp(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __res
 //   COMPACT = true   bits[W/32] plus one prefix per FOUR words (5 B per 32 columns): 1,048,576 columns fit one
 //                    160 KB table, one 1024-thread block per SM, a 128-bit shared load per rank.
 // Matrices wider than the table take several column windows.
-// (A variant that accumulated by rank in shared memory, in rank windows, measured slower than the L2 reductions
-//  on every config and was removed -- DESIGN.md section 7.)
+// (Two variants measured slower and were removed -- DESIGN.md section 7: accumulating by rank in shared memory, in
+//  rank windows (round 1), and a block-wide shared-memory hash table of (column, value) scattered by bitmap rank,
+//  one traversal of the products instead of two (round 2: cfg 4r numeric 6.7 ms against 3.6 ms, barrier stalls and
+//  compare-and-swap contention on the hub columns of power-law inputs; profiles/r2/numeric_hash_bins.md).)
 template <bool COMPACT>
 struct RankTable {
     unsigned* bits;      // COMPACT: bits[words];            else: interleaved {bits, prefix}
@@ -331,105 +330,6 @@ k_numeric_rank(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __res
     }
 }
 
-// Numeric, block per row, rows whose exact nnz fits a shared-memory hash table at <= 75 % load.
-// One traversal of the row's products (the rank kernel above makes two, on top of the symbolic phase's one):
-//   accumulate  every product goes into an open-addressing table of (column, float64 sum); the thread that
-//               inserts a new column also sets its bit in the column bitmap;
-//   prefix      exclusive popcount prefix over the bitmap: rank(c) = position of column c in the sorted row;
-//   scatter     every occupied slot writes (column, sum) to C at row_offset + rank(column).
-// The sums are built in shared memory (scripts/micro/atomic_bw.cu: 540 G float64 adds/s chip-wide against 197 G/s for
-// L2 reductions) and C is written once with plain stores.  Shared memory: vals[SLOTS] | keys[SLOTS] | rank table.
-template <bool COMPACT, int THREADS, int SLOTS>
-__global__ void __launch_bounds__(THREADS)
-k_numeric_hash(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __restrict__ b_sorted_flag,
-               const int32_t* __restrict__ list, int count, int window,
-               const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, double* __restrict__ c_val,
-               int32_t* __restrict__ work_counter) {
-    extern __shared__ __align__(16) unsigned char s_dynb[];
-    double* vals = reinterpret_cast<double*>(s_dynb);
-    int* keys = reinterpret_cast<int*>(vals + SLOTS);
-    RankTable<COMPACT> tab;
-    tab.bits = reinterpret_cast<unsigned*>(keys + SLOTS);
-    tab.pre = tab.bits + (window >> 5);            // COMPACT only
-    __shared__ int s_item;
-    __shared__ int s_red[33];
-    __shared__ SegScratch<THREADS> s_seg;
-    const bool b_sorted = *b_sorted_flag != 0;
-    const int n = B.cols;
-    while (true) {
-        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
-        __syncthreads();
-        const int item = s_item;
-        __syncthreads();
-        if (item >= count) break;
-        const int r = __ldg(list + item), i = row_begin + r;
-        const int a_begin = __ldg(A.ptr + i), a_end = __ldg(A.ptr + i + 1);
-        const int lo = upper_only ? i : 0;
-        int64_t out = __ldg(c_ptr + r);
-        for (int w0 = (lo / window) * window; w0 < n; w0 += window) {
-            const int wl = max(w0, lo), wh = min(w0 + window, n);
-            const int words = (((wh - w0 + 31) >> 5) + 3) & ~3;
-            const bool col_windowed = upper_only || window < n;
-            if (COMPACT) for (int t = threadIdx.x; t < words; t += THREADS) tab.bits[t] = 0u;
-            else for (int t = threadIdx.x; t < words; t += THREADS) reinterpret_cast<uint2*>(tab.bits)[t] = make_uint2(0u, 0u);
-            for (int t = threadIdx.x; t < SLOTS; t += THREADS) { keys[t] = kEmpty; vals[t] = 0.0; }
-            __syncthreads();
-            expand_row_block<true>(A, B, a_begin, a_end, wl, wh, col_windowed, b_sorted, s_seg, [&](int c, double v) {
-                unsigned h = hash_slot(c, SLOTS);
-                while (true) {
-                    const int k = *((volatile int*)(keys + h));
-                    if (k == c) break;
-                    if (k == kEmpty) {
-                        const int old = atomicCAS(keys + h, kEmpty, c);
-                        if (old == kEmpty) {                   // first insertion of this column: mark it
-                            const int o = c - w0;
-                            atomicOr(tab.word_ptr(o >> 5), 1u << (o & 31));
-                            break;
-                        }
-                        if (old == c) break;
-                    }
-                    h = (h + 1 == SLOTS) ? 0 : h + 1;
-                }
-                atomicAdd(vals + h, v);
-            });
-            __syncthreads();
-            // exclusive popcount prefix (per word, or per group of four words)
-            const int units = COMPACT ? words >> 2 : words;
-            int nnz_w = 0;
-            for (int base = 0; base < units; base += THREADS) {
-                const int u = base + threadIdx.x;
-                int pc = 0;
-                if (u < units) {
-                    if (COMPACT) {
-                        const uint4 b = reinterpret_cast<const uint4*>(tab.bits)[u];
-                        pc = __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
-                    } else {
-                        pc = __popc(tab.bits[2 * u]);
-                    }
-                }
-                int tot;
-                const int ex = block_excl_scan<int>(pc, s_red, &tot);
-                if (u < units) {
-                    if (COMPACT) tab.pre[u] = (unsigned)(nnz_w + ex); else tab.bits[2 * u + 1] = (unsigned)(nnz_w + ex);
-                }
-                nnz_w += tot;
-            }
-            __syncthreads();
-            // scatter the table to its sorted place
-            for (int t = threadIdx.x; t < SLOTS; t += THREADS) {
-                const int k = keys[t];
-                if (k != kEmpty) {
-                    const int64_t pos = out + tab.rank(k - w0);
-                    c_idx[pos] = k;
-                    c_val[pos] = vals[t];
-                }
-            }
-            out += nnz_w;
-            __syncthreads();
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // host side
 static size_t g_smem_optin = 0;
@@ -449,54 +349,7 @@ cudaError_t sparse_kernels_configure() {
     e = cudaFuncSetAttribute(k_numeric_rank<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20480);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_numeric_rank<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 24576);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_numeric_hash<false, 512, kHashSlots4K>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 12288);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_numeric_hash<true, 1024, kHashSlotsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 22528);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_numeric_hash<false, 1024, kHashSlots12K>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 22528);
     return e;
-}
-
-// Shared-memory plan of the block-hash bins for a result with `cols` columns (the rank table covers every column
-// of the window; the hash table sits beside it):
-//   narrow  pair table (8 B per 32 columns) + 4,096 slots, 512 threads, several blocks per SM; 12,288 slots, 1024
-//           threads, one block per SM
-//   wide    compact table (5 B per 32 columns, up to 2^20 columns per window) + 3,584 slots, 1024 threads, one block
-//           per SM; no 12,288-slot bin (its rows stay in the rank bin)
-struct HashPlan {
-    bool narrow;
-    size_t table_bytes;       // rank table of one window
-    int window;               // columns per window
-};
-static HashPlan hash_plan(int cols) {
-    const int64_t c128 = ((int64_t)cols + 127) & ~(int64_t)127;
-    const size_t static12k = 22528, hash12k = (size_t)kHashSlots12K * 12;
-    HashPlan p;
-    p.narrow = (size_t)(c128 / 4) + hash12k + static12k <= g_smem_optin;
-    if (p.narrow) {
-        p.table_bytes = (size_t)(c128 / 4);
-        p.window = (int)c128;
-    } else {
-        // largest window (multiple of 128 columns, at most 2^20) whose compact table fits beside the wide hash table
-        const int64_t fit = (int64_t)((g_smem_optin - static12k - (size_t)kHashSlotsWide * 12) * 32 / 5) & ~(int64_t)127;
-        int64_t window = c128 < (1 << 20) ? c128 : (1 << 20);
-        if (window > fit) window = fit;
-        p.table_bytes = (size_t)(window / 8 + window / 32);
-        p.window = (int)window;
-    }
-    return p;
-}
-
-void numeric_hash_caps(int cols, int* cap_h4k, int* cap_h12k) {
-    const HashPlan p = hash_plan(cols);
-    *cap_h4k = p.narrow ? kHashCap4K : kHashCapWide;
-    *cap_h12k = p.narrow ? kHashCap12K : 0;
-    // experiments: SPGEMM_B200_HASH_BINS bit 0 = 4,096-slot bin, bit 1 = 12,288-slot bin (others go to the rank bin)
-    int bins = 3;
-    if (const char* v = getenv("SPGEMM_B200_HASH_BINS")) bins = atoi(v);
-    if (!(bins & 1)) *cap_h4k = 0;
-    if (!(bins & 2)) *cap_h12k = 0;
 }
 
 // Run up to three independent bin kernels on side streams: fork after everything queued on the main stream so
@@ -586,7 +439,7 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
     const size_t stride = (size_t)job.nrows;
     const int cap = lc.sm_count * 16;
     const int nonempty = (h_counts[NUM_W64] != 0) + (h_counts[NUM_W256] != 0) + (h_counts[NUM_W1K] != 0) +
-                         (h_counts[NUM_H4K] != 0) + (h_counts[NUM_H12K] != 0) + (h_counts[NUM_RANK] != 0);
+                         (h_counts[NUM_RANK] != 0);
     Fork fork(lc);
     const bool conc = nonempty > 1;
     if (h_counts[NUM_W64]) {
@@ -609,34 +462,6 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
             job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_W1K * stride, h_counts[NUM_W1K], c_ptr,
             c_idx, c_val);
         SB_LAUNCH_CHECK(lc);
-    }
-    if (h_counts[NUM_H4K] || h_counts[NUM_H12K]) {
-        const HashPlan plan = hash_plan(job.B.cols);
-        cudaError_t e = cudaMemsetAsync(d_work_counter + 1, 0, 2 * sizeof(int32_t), lc.stream);
-        if (e != cudaSuccess) return e;
-        if (h_counts[NUM_H4K]) {
-            const size_t smem = (size_t)(plan.narrow ? kHashSlots4K : kHashSlotsWide) * 12 + plan.table_bytes;
-            if (plan.narrow) {
-                int per_sm = (int)((g_smem_optin + 1024) / (smem + 12288));
-                if (per_sm > 4) per_sm = 4;
-                if (per_sm < 1) per_sm = 1;
-                k_numeric_hash<false, 512, kHashSlots4K><<<grid_for(h_counts[NUM_H4K], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
-                    job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_H4K * stride, h_counts[NUM_H4K],
-                    plan.window, c_ptr, c_idx, c_val, d_work_counter + 1);
-            } else {
-                k_numeric_hash<true, 1024, kHashSlotsWide><<<grid_for(h_counts[NUM_H4K], 1, lc.sm_count), 1024, smem, lc.stream>>>(
-                    job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_H4K * stride, h_counts[NUM_H4K],
-                    plan.window, c_ptr, c_idx, c_val, d_work_counter + 1);
-            }
-            SB_LAUNCH_CHECK(lc);
-        }
-        if (h_counts[NUM_H12K]) {                         // narrow plan only (numeric_hash_caps)
-            const size_t smem = (size_t)kHashSlots12K * 12 + plan.table_bytes;
-            k_numeric_hash<false, 1024, kHashSlots12K><<<grid_for(h_counts[NUM_H12K], 1, lc.sm_count), 1024, smem, lc.stream>>>(
-                job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_H12K * stride, h_counts[NUM_H12K],
-                plan.window, c_ptr, c_idx, c_val, d_work_counter + 2);
-            SB_LAUNCH_CHECK(lc);
-        }
     }
     if (h_counts[NUM_RANK]) {
         cudaError_t e = cudaMemsetAsync(d_work_counter, 0, sizeof(int32_t), lc.stream);

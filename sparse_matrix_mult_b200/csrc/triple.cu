@@ -7,10 +7,14 @@
 // C[i,k] += w * h_kc for k >= i.  Work is P1 + P2 instead of n^2/2 * nnz/row, H Q is never
 // materialised, and every byte of C is written once.
 //
-// k_triple_panels (default): C is built one column panel at a time; a block owns a (panel, row) segment of up to
-// ~26,800 doubles in SHARED memory, so every add is a shared-memory add (scripts/micro/atomic_bw.cu: 540 G float64
-// adds/s chip-wide against 197 G/s for L2 reductions), and the slice of H^T a panel gathers from stays in L2.
-// k_triple_rows_red (round 1, kept selectable for A/B runs: SPGEMM_B200_TRIPLE_MODE=2): every add is an L2 reduction.
+// C is built one column panel at a time; a block owns a (panel, row) segment of up to ~26,800 doubles in SHARED memory,
+// so every add is a shared-memory add (scripts/micro/atomic_bw.cu: 540 G float64 adds/s chip-wide against 197 G/s for
+// L2 reductions), and the slice of H^T a panel gathers from stays in L2.  Two kernels share that structure:
+//   k_triple_runs    every row of Q is one run of consecutive columns (banded covariance): a warp streams one
+//                    contiguous range of H^T per entry of H and looks the weight up by the column stored with the entry
+//   k_triple_panels  any Q: the rows of H^T of 32 products at a time are walked as one flat, balanced stream
+// (The round-1 kernel -- a row of C in global memory, every add an L2 reduction, one gather walk per thread -- measured
+//  23.2 ms on cfg 5 against 13.9 ms / 21.6 ms for these two: profiles/r2/triple_kernel_history.md.)
 #include <cstdlib>
 
 #include "internal.h"
@@ -425,18 +429,36 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
                     // next step are in flight while the current step is multiplied and added (ranges are ~100-200
                     // entries long: wider steps would leave most lanes of the last one idle)
                     int x = es + lane;
-                    int2 kc = x < ee ? ld_keep_i2(t_kc + x, keep) : make_int2(-1, 0);
-                    double v = x < ee ? ld_keep_f64(t_val + x, keep) : 0.0;
-                    for (; x < ee; x += 32) {
-                        const int xn = x + 32;
-                        const int2 kcn = xn < ee ? ld_keep_i2(t_kc + xn, keep) : make_int2(-1, 0);
-                        const double vn = xn < ee ? ld_keep_f64(t_val + xn, keep) : 0.0;
-                        if (!filtered || kc.x >= lo) {
+                    const int2* pk = t_kc + x;
+                    const double* pv = t_val + x;
+                    int2 kc = x < ee ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
+                    double v = x < ee ? ld_keep_f64(pv, keep) : 0.0;
+                    if (!filtered) {
+                        for (; x < ee; x += 32) {
+                            pk += 32;
+                            pv += 32;
+                            const bool more = x + 32 < ee;
+                            const int2 kcn = more ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
+                            const double vn = more ? ld_keep_f64(pv, keep) : 0.0;
                             atomicAdd(acc + (kc.x - lo), wt[kc.y] * v);
-                            ++p2;
+                            kc = kcn;
+                            v = vn;
                         }
-                        kc = kcn;
-                        v = vn;
+                        if (lane == 0) p2 += (unsigned)(ee - es);
+                    } else {
+                        for (; x < ee; x += 32) {
+                            pk += 32;
+                            pv += 32;
+                            const bool more = x + 32 < ee;
+                            const int2 kcn = more ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
+                            const double vn = more ? ld_keep_f64(pv, keep) : 0.0;
+                            if (kc.x >= lo) {
+                                atomicAdd(acc + (kc.x - lo), wt[kc.y] * v);
+                                ++p2;
+                            }
+                            kc = kcn;
+                            v = vn;
+                        }
                     }
                     __syncwarp();                          // the table is rewritten by the next piece
                 }
@@ -460,48 +482,6 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
         if (tail < count && tid == nt - 1) { st_stream_f64(dst + tail, acc[tail]); acc[tail] = 0.0; }
     }
     triple_flush_counters(p1, p2_total, S.cnt, counters);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Round-1 kernel: the block owns a whole row of C in global memory, streams zeros over it and adds every
-// contribution with a float64 reduction that resolves in L2.  The rows being accumulated must stay L2 resident
-// (a reduction that misses L2 is a DRAM read-modify-write), so the grid is persistent and sized so that
-// rows-in-flight x 8n bytes fits a share of the 126 MB L2.
-template <bool UPPER, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-k_triple_rows_red(Csr H, Csr Q, Csr Ht, int ht_desc, int row_begin, int nrows,
-                  double* __restrict__ C, unsigned long long* __restrict__ counters) {
-    __shared__ unsigned long long s_cnt[2];
-    __shared__ SegScratch<THREADS> s_seg;
-    const int n = H.rows;
-    const bool desc = ht_desc != 0;
-    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    unsigned long long p1 = 0, p2 = 0;
-    __shared__ int s_row;
-    while (true) {
-        if (threadIdx.x == 0) s_row = (int)atomicAdd(counters + 2, 1ULL);
-        __syncthreads();
-        const int r = s_row;
-        __syncthreads();
-        if (r >= nrows) break;
-        const int i = row_begin + r;
-        const int lo = UPPER ? i : 0;
-        double* row = C + (size_t)r * n;
-        triple_stream_out(row, nullptr, n);
-        expand_row_block<true>(H, Q, __ldg(H.ptr + i), __ldg(H.ptr + i + 1), 0, 0, false, false, s_seg,
-                               [&](int c, double w) {
-                                   ++p1;
-                                   const int s = __ldg(Ht.ptr + c), e = __ldg(Ht.ptr + c + 1);
-                                   for (int q = s; q < e; ++q) {
-                                       const int k = __ldg(Ht.idx + q);
-                                       if (k < lo) { if (desc) break; else continue; }
-                                       atomicAdd(row + k, w * __ldg(Ht.val + q));
-                                       ++p2;
-                                   }
-                               });
-    }
-    triple_flush_counters(p1, p2, s_cnt, counters);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -597,35 +577,6 @@ cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q
             k_triple_panels<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
         else
             k_triple_panels<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
-    }
-    SB_LAUNCH_CHECK(lc);
-    return cudaSuccess;
-}
-
-// Round-1 kernel (SPGEMM_B200_TRIPLE_MODE=2): Ht is the plain transpose of H.
-cudaError_t launch_triple_red(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool ht_desc,
-                              bool upper_only, int row_begin, int nrows, double* d_c, unsigned long long* d_counters) {
-    const int n = H.rows;
-    if (nrows <= 0 || n <= 0) return cudaSuccess;
-    const double l2_budget = 64.0e6;                                  // bytes of C rows in flight
-    const double row_bytes = 8.0 * n * (upper_only ? 0.6 : 1.0);      // upper rows touch [i, n) only
-    int rows_in_flight = (int)(l2_budget / row_bytes);
-    if (rows_in_flight < lc.sm_count) rows_in_flight = lc.sm_count;
-    const bool big = rows_in_flight < lc.sm_count * 4;                // few rows allowed: fat blocks
-    const int per_sm = big ? 1 : (rows_in_flight / lc.sm_count > 8 ? 8 : rows_in_flight / lc.sm_count);
-    int grid = lc.sm_count * per_sm;
-    if (grid > nrows) grid = nrows;
-    const int d = ht_desc ? 1 : 0;
-    if (big) {
-        if (upper_only)
-            k_triple_rows_red<true, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
-        else
-            k_triple_rows_red<false, 1024><<<grid, 1024, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
-    } else {
-        if (upper_only)
-            k_triple_rows_red<true, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
-        else
-            k_triple_rows_red<false, 256><<<grid, 256, 0, lc.stream>>>(H, Q, Ht, d, row_begin, nrows, d_c, d_counters);
     }
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
