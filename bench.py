@@ -310,7 +310,8 @@ class Resident:
             # flop-balanced partition from the GPU cost pass (the multi-GPU replacement of limits())
             ht = self.A.transpose() if self.kind == "triple" else None
             costs, _ = dev.row_costs(self.A, ht if ht is not None else self.B, self.B if ht is not None else None,
-                                     upper_only=(self.kind == "triple" or self.sym))
+                                     upper_only=(self.kind == "triple" or self.sym),
+                                     dense_cols=(self.ncols if self.kind == "dense" else 0))
             self.bounds = [int(x) for x in dev.partition_rows(costs, self.n_rows, world)]
             self.lib.spgemm_b200_device_free(costs)
             if ht is not None:
@@ -418,6 +419,8 @@ def e2e_single_process(w, flops, steps, warm, n_gpus):
             d2h = sum(int(s["bytes_d2h"]) for s in per) or d2h_bytes
             device_ms = {k: round(max(s[k] for s in per), 3) for k in
                          ("ms_h2d", "ms_analysis", "ms_symbolic", "ms_numeric", "ms_post", "ms_d2h", "ms_total")}
+            device_ms["per_gpu"] = [{k: round(s[k], 3) if k.startswith("ms") else int(s[k]) for k in
+                                     ("ms_h2d", "ms_analysis", "ms_numeric", "ms_d2h", "bytes_d2h")} for s in per]
         else:
             st = dev.last_stats()           # of the last end-to-end call: bytes that actually crossed PCIe
             h2d, d2h = int(st["bytes_h2d"]), int(st["bytes_d2h"])

@@ -209,11 +209,13 @@ SPGEMM_B200_API int spgemm_b200_mirror_dev(double *d_c, int n);
 /* In place on an n x n device matrix: C = C + C^T - diag(C). */
 SPGEMM_B200_API int spgemm_b200_symmetrize_dev(double *d_c, int n);
 
-/* Per-row intermediate-product counts of rows of A against B (int64[rows(A)], device) and their total:
-   the flop-counting pass that replaces limits() (src/workdivision.cpp:16-89).  For the triple product pass
-   q != NULL: cost_i = P1_i + P2_i(upper) of H = a, Q = q, H^T = b.  Either output may be NULL. */
+/* Per-row cost of rows of A against B (int64[rows(A)], device) and their total: the flop-counting pass that replaces
+   limits() (src/workdivision.cpp:16-89).  Sparse / dense output: the intermediate-product count P_i of the row, plus
+   0.3 * dense_cols when the output row is a dense row of dense_cols doubles written in full (pass 0 for sparse output).
+   Triple product (q != NULL; a = H, q = Q, b = H^T as built by spgemm_b200_mat_transpose):
+   cost_i = a P1_i panels(i) + b P2_i (n - i)/n + c n, see k_triple_costs.  Either output may be NULL. */
 SPGEMM_B200_API int spgemm_b200_row_costs(const spgemm_b200_mat *a, const spgemm_b200_mat *b, const spgemm_b200_mat *q,
-                          int upper_only, int64_t *d_costs, int64_t *total_host);
+                          int upper_only, int dense_cols, int64_t *d_costs, int64_t *total_host);
 
 /* Flop-balanced contiguous row partition: bounds[parts+1] (host) with bounds[0] = 0, bounds[parts] = rows,
    chosen so every part carries ~total/parts of d_costs.  Replaces limits() for multi-GPU sharding. */

@@ -507,14 +507,30 @@ cudaError_t launch_narrow_indptr(const LaunchCtx& lc, const int64_t* in, int32_t
 }
 
 // ---------------------------------------------------------------------------------------------------
+// costs[i] += c: the part of a row's cost that does not depend on its products (a dense output row is written in
+// full, zeros included: for BASELINE config 2 that is all of the time).
+__global__ void __launch_bounds__(256)
+k_add_const(int64_t* __restrict__ costs, int n, long long c) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) costs[t] += c;
+}
+cudaError_t launch_add_const(const LaunchCtx& lc, int64_t* d_costs, int n, long long c) {
+    if (n <= 0 || c == 0) return cudaSuccess;
+    k_add_const<<<(n + 255) / 256, 256, 0, lc.stream>>>(d_costs, n, c);
+    SB_LAUNCH_CHECK(lc);
+    return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Cost of row i of the triple product H Q H^T for the flop-balanced multi-GPU split:
 //   P1_i = sum over (i,j) in H of nnz(Q[j,:])                         (expansion of H[i,:] Q)
 //   P2_i = sum over those (j,c) of nnz(H^T[c,:])                      (entries of H^T the contraction streams)
-// cost_i = a * P1_i * panels(i) + b * P2_i + c * P2_i * (n - i) / n: every product pays its gathers of Q and of the
-// extent of its row of H^T once per column panel the row takes part in (a; upper mode: the panels right of the
-// diagonal), every entry of H^T in those panels is read and tested against the diagonal (b), and the fraction
-// (n - i) / n that survives the k >= i cut of the upper-triangle mode is multiplied and accumulated (c).
-// (a, b, c) are fitted to the per-rank kernel times of cfg 5 (profiles/r2); SPGEMM_B200_TRIPLE_COST="a,b,c"
+// cost_i = a * P1_i * panels(i) + b * P2_i * (n - i) / n + c * n: the expansion is redone for every column panel
+// the row takes part in (a; upper mode: the panels right of the diagonal), the entries of H^T in those panels --
+// the fraction (n - i) / n of all of them in upper mode -- are multiplied and accumulated (b), and every row of C is
+// written in full, zeros included (c).  (a, b, c) were fitted to the per-rank kernel times of cfg 5 on four B200s
+// (profiles/r2/multi_gpu.md): (0.005, 0.53, 0.25) ms per 10^8 units with the banded-Q kernel, i.e. the expansion is
+// almost free there; the general kernel pays ~100 instructions per 32 products.  SPGEMM_B200_TRIPLE_COST="a,b,c"
 // overrides them.  One warp per row.
 __global__ void __launch_bounds__(256)
 k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, int np, int panel_w, double ca, double cb, double cc,
@@ -533,13 +549,13 @@ k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, int np, int panel_w, double
         const double keep = upper_only ? (double)(H.rows - row) / (double)H.rows : 1.0;
         const int panels = upper_only ? np - row / panel_w : np;
         costs[row] = (long long)(ca * (double)p1 * (double)(panels > 1 ? panels : 1) + cb * (double)p2 * keep +
-                                 cc * (double)p2 * keep);
+                                 cc * (double)H.rows);
     }
 }
 cudaError_t launch_triple_costs(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool upper_only,
-                                int np, int panel_w, int64_t* d_costs) {
+                                bool q_runs, int np, int panel_w, int64_t* d_costs) {
     if (H.rows <= 0) return cudaSuccess;
-    double ca = 4.0, cb = 1.0, cc = 2.0;
+    double ca = q_runs ? 0.05 : 2.0, cb = 1.0, cc = 0.5;
     if (const char* v = getenv("SPGEMM_B200_TRIPLE_COST")) sscanf(v, "%lf,%lf,%lf", &ca, &cb, &cc);
     k_triple_costs<<<(H.rows + 7) / 8, 256, 0, lc.stream>>>(H, Q, Ht, upper_only ? 1 : 0, np, panel_w > 0 ? panel_w : 1,
                                                            ca, cb, cc, d_costs);

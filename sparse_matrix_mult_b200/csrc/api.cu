@@ -504,44 +504,50 @@ static void zero_nt(double* p, size_t count) {
 }
 
 // Device -> host copy of rows [r0, r1) of an n-column result whose entries left of the diagonal are known to be
-// zero (symmetric dense mode, triple product): only the upper trapezoids cross PCIe -- the row block starting at
-// row b sends columns [b, n) as one 2-D copy -- while host threads zero the rectangles to their left.  Halves
-// the bytes on the link, which is what bounds these modes end to end.  d_c holds rows [r0, r1) only; c_host is
-// the full n-column host matrix.
-cudaError_t d2h_upper_rows(const double* d_c, int n, int r0, int r1, double* c_host) {
+// zero (symmetric dense mode, triple product): only the upper trapezoids cross PCIe, host threads zero the rest.
+// The n rows are cut into fixed row blocks of kUpperBlocks-th of the matrix; block g (rows [gG, (g+1)G)) sends
+// columns [gG, n) as one 2-D copy and has columns [0, gG) zeroed on the host.  Halves the bytes on the link.
+// The zero fill is work any thread can do whoever owns the rows: share `part` of `nparts` (the multi-GPU driver
+// passes its GPU's index so the lower triangle is split evenly over all workers; one GPU: 0 of 1) takes the blocks
+// g = part (mod nparts), on `SPGEMM_B200_ZERO_THREADS` threads (default: the host's cores / nparts, at most 32).
+// d_c holds rows [r0, r1) only; c_host is the full n-column host matrix.
+constexpr int kUpperBlocks = 256;
+
+cudaError_t d2h_upper_rows(const double* d_c, int n, int r0, int r1, double* c_host, int part, int nparts) {
     Ctx& g = cx();
-    const int rows = r1 - r0;
-    if (n <= 0 || rows <= 0) return cudaSuccess;
-    const int blocks = rows < 64 ? 1 : 64;
-    const int step = (rows + blocks - 1) / blocks;
+    if (n <= 0) return cudaSuccess;
+    const int G = (n + kUpperBlocks - 1) / kUpperBlocks;          // rows per block
     cudaError_t err = cudaSuccess;
-    for (int b0 = r0; b0 < r1 && err == cudaSuccess; b0 += step) {
-        const int b1 = b0 + step < r1 ? b0 + step : r1;
-        const int c0 = b0 < n ? b0 : n;                       // first column that can be non-zero in this block
-        if (c0 < n)
-            err = cudaMemcpy2DAsync(c_host + (size_t)b0 * n + c0, (size_t)n * 8, d_c + (size_t)(b0 - r0) * n + c0,
-                                    (size_t)n * 8, (size_t)(n - c0) * 8, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, g.stream);
-        g.stats.bytes_d2h += (int64_t)(n - c0) * (b1 - b0) * 8;
+    for (int b0 = (r0 / G) * G; b0 < r1 && err == cudaSuccess; b0 += G) {
+        const int s0 = b0 > r0 ? b0 : r0, s1 = b0 + G < r1 ? b0 + G : r1;     // this call's rows of the block
+        if (s1 <= s0) continue;
+        err = cudaMemcpy2DAsync(c_host + (size_t)s0 * n + b0, (size_t)n * 8, d_c + (size_t)(s0 - r0) * n + b0,
+                                (size_t)n * 8, (size_t)(n - b0) * 8, (size_t)(s1 - s0), cudaMemcpyDeviceToHost, g.stream);
+        g.stats.bytes_d2h += (int64_t)(n - b0) * (s1 - s0) * 8;
     }
-    // zero the lower-left rectangles on the host meanwhile (row blocks interleaved over the threads)
+    // zero this share of the lower-left rectangles on the host meanwhile
     unsigned hw = std::thread::hardware_concurrency();
-    int nthreads = hw == 0 ? 4 : (hw > 8 ? 8 : (int)hw);     // measured: flat beyond 4-8 threads (~40 GB/s)
+    int nthreads = hw == 0 ? 4 : (int)hw / (nparts > 0 ? nparts : 1);
+    if (nthreads > 32) nthreads = 32;
+    if (nthreads < 1) nthreads = 1;
     if (const char* ev = getenv("SPGEMM_B200_ZERO_THREADS")) nthreads = atoi(ev);      // 0 = skip (experiments only)
-    if ((size_t)rows * n < ((size_t)1 << 22) && nthreads > 1) nthreads = 1;
-    auto zero_rows = [=](int t) {
-        int b = 0;
-        for (int b0 = r0; b0 < r1; b0 += step, ++b) {
-            if (b % nthreads != t || b0 == 0) continue;
-            const int b1 = b0 + step < r1 ? b0 + step : r1;
-            const int c0 = b0 < n ? b0 : n;
-            for (int r = b0; r < b1; ++r) zero_nt(c_host + (size_t)r * n, (size_t)c0);
+    if ((size_t)n * n < ((size_t)1 << 22) && nthreads > 1) nthreads = 1;
+    if (nthreads <= 0) return err;
+    const int nblocks = (n + G - 1) / G;
+    auto zero_blocks = [=](int t) {
+        // blocks of this share, dealt to the threads from the bottom of the matrix up (widest rectangles first)
+        int k = 0;
+        for (int gb = nblocks - 1; gb >= 1; --gb) {
+            if (gb % nparts != part) continue;
+            if (k++ % nthreads != t) continue;
+            const int b0 = gb * G, b1 = b0 + G < n ? b0 + G : n;
+            for (int r = b0; r < b1; ++r) zero_nt(c_host + (size_t)r * n, (size_t)b0);
         }
         _mm_sfence();
     };
-    if (nthreads <= 0) return err;
     std::vector<std::thread> pool;
-    for (int t = 1; t < nthreads; ++t) pool.emplace_back(zero_rows, t);
-    zero_rows(0);
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(zero_blocks, t);
+    zero_blocks(0);
     for (auto& th : pool) th.join();
     return err;
 }
@@ -726,7 +732,7 @@ int triple_rows(const spgemm_b200_mat* h, const spgemm_b200_mat* q, const spgemm
 }
 
 int row_costs_impl(const spgemm_b200_mat* a, const spgemm_b200_mat* b, const spgemm_b200_mat* q, int upper_only,
-                   int64_t* costs) {
+                   int dense_cols, int64_t* costs) {
     Ctx& g = cx();
     const int m = a->rows;
     LaunchCtx lc = lctx();
@@ -734,7 +740,8 @@ int row_costs_impl(const spgemm_b200_mat* a, const spgemm_b200_mat* b, const spg
     int32_t* ws = nullptr;
     if (q) {
         const TriplePlan plan = triple_plan(a->rows, 0, upper_only != 0, a->nnz, a->cols);
-        e = launch_triple_costs(lc, view(a), view(q), view(b), upper_only != 0, plan.np, plan.panel_w, costs);
+        e = launch_triple_costs(lc, view(a), view(q), view(b), upper_only != 0, q->checked && q->runs, plan.np,
+                                plan.panel_w, costs);
     } else {
         int rc = dalloc(&ws, (size_t)m + (size_t)SYM_BINS * m + 32);
         if (rc) return rc;
@@ -744,6 +751,9 @@ int row_costs_impl(const spgemm_b200_mat* a, const spgemm_b200_mat* b, const spg
         if (e == cudaSuccess)
             e = launch_row_products(lc, view(a), view(b), 0, m, upper_only != 0, costs, ws, ws + m, small,
                                     reinterpret_cast<unsigned long long*>(small + 24));
+        // dense output: a row of `dense_cols` doubles is written whatever its products (one product ~ 3 doubles written:
+        // 5 ps per L2 reduction against 1.6 ps per streamed double)
+        if (e == cudaSuccess && dense_cols > 0) e = launch_add_const(lc, costs, m, (long long)(0.3 * dense_cols) + 1);
     }
     dfree(ws);
     if (e != cudaSuccess) return fail(SPGEMM_B200_ERR_CUDA, "row_costs", e);
@@ -1060,7 +1070,7 @@ int spgemm_b200_dense(int m, int k, int n, const int32_t* a_indptr, const int32_
     mark(EV_POST);
     if (elems) {
         NvtxRange nv("spgemm_b200:d2h");
-        if (upper_only && !mirror && m == n) e = d2h_upper_rows(d_c, n, 0, n, c_host);
+        if (upper_only && !mirror && m == n) e = d2h_upper_rows(d_c, n, 0, n, c_host, 0, 1);
         else { e = cudaMemcpyAsync(c_host, d_c, elems * 8, cudaMemcpyDeviceToHost, g.stream); g.stats.bytes_d2h += (int64_t)elems * 8; }
         if (e != cudaSuccess) return done(fail(SPGEMM_B200_ERR_CUDA, "dense result copy", e));
     }
@@ -1146,7 +1156,7 @@ int spgemm_b200_triple(int n, int k, const int32_t* h_indptr, const int32_t* h_i
     e = cudaMemcpyAsync(hc, d_cnt, 16, cudaMemcpyDeviceToHost, g.stream);
     if (e == cudaSuccess && elems) {
         NvtxRange nv("spgemm_b200:d2h");
-        if (mode == SPGEMM_B200_TRIPLE_UPPER) e = d2h_upper_rows(d_c, n, 0, n, c_host);
+        if (mode == SPGEMM_B200_TRIPLE_UPPER) e = d2h_upper_rows(d_c, n, 0, n, c_host, 0, 1);
         else { e = cudaMemcpyAsync(c_host, d_c, elems * 8, cudaMemcpyDeviceToHost, g.stream); g.stats.bytes_d2h += (int64_t)elems * 8; }
     }
     mark(EV_D2H);
@@ -1208,7 +1218,7 @@ int spgemm_b200_copy_upper_to_host(double* host_dst, const double* d_src, int n)
     if (n > 0 && (!host_dst || !d_src)) return fail(SPGEMM_B200_ERR_ARG, "copy_upper_to_host: null pointer");
     ENTER_DEFAULT();
     cx().stats.bytes_d2h = 0;
-    CU(d2h_upper_rows(d_src, n, 0, n, host_dst));
+    CU(d2h_upper_rows(d_src, n, 0, n, host_dst, 0, 1));
     CU(cudaStreamSynchronize(cx().stream));
     return SPGEMM_B200_OK;
 }
@@ -1303,7 +1313,7 @@ int spgemm_b200_flush_l2(void) {
 
 // ---- row costs / partition ------------------------------------------------------------------------------
 int spgemm_b200_row_costs(const spgemm_b200_mat* a, const spgemm_b200_mat* b, const spgemm_b200_mat* q, int upper_only,
-                          int64_t* d_costs, int64_t* total_host) {
+                          int dense_cols, int64_t* d_costs, int64_t* total_host) {
     if (!a || !b) return fail(SPGEMM_B200_ERR_ARG, "row_costs: null matrix");
     ENTER_DEVICE(a->device);
     Ctx& g = cx();
@@ -1313,7 +1323,7 @@ int spgemm_b200_row_costs(const spgemm_b200_mat* a, const spgemm_b200_mat* b, co
     const int m = a->rows;
     int64_t* costs = d_costs;
     if (!costs && (rc = dalloc(&costs, (size_t)m))) return rc;
-    rc = row_costs_impl(a, b, q, upper_only, costs);
+    rc = row_costs_impl(a, b, q, upper_only, dense_cols, costs);
     cudaError_t e = cudaSuccess;
     if (!rc && total_host) {
         std::vector<int64_t> hc((size_t)m);          // total on the host (setup path, not timed)

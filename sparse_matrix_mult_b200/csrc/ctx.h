@@ -132,11 +132,12 @@ int dense_rows(spgemm_b200_mat* a, spgemm_b200_mat* b, int upper_only, int r0, i
 int triple_rows(const spgemm_b200_mat* h, const spgemm_b200_mat* q, const spgemm_b200_mat* ht, int upper_only, int r0,
                 int r1, double* d_c, unsigned long long* d_cnt);
 int row_costs_impl(const spgemm_b200_mat* a, const spgemm_b200_mat* b, const spgemm_b200_mat* q, int upper_only,
-                   int64_t* d_costs);
+                   int dense_cols, int64_t* d_costs);
 void partition_costs(const int64_t* costs, int rows, int parts, int32_t* bounds);
 // rows [r0, r1) of an n-column result whose entries left of the diagonal are zero: columns [block start, n) of
-// each row block cross PCIe, host threads zero the rest.  d_c holds the rows [r0, r1) only.
-cudaError_t d2h_upper_rows(const double* d_c, int n, int r0, int r1, double* c_host);
+// each fixed row block cross PCIe; this caller's share (part of nparts) of the lower triangle is zeroed by host
+// threads.  d_c holds the rows [r0, r1) only.
+cudaError_t d2h_upper_rows(const double* d_c, int n, int r0, int r1, double* c_host, int part, int nparts);
 
 // pinned host cache (process-wide)
 void* host_cache_alloc(size_t bytes);

@@ -68,9 +68,10 @@ cudaError_t launch_sort_rows(const LaunchCtx& lc, int rows, const int32_t* ptr, 
                              int32_t* d_long_list, bool descending);
 cudaError_t launch_narrow_indptr(const LaunchCtx& lc, const int64_t* in, int32_t* out, int n);
 
+cudaError_t launch_add_const(const LaunchCtx& lc, int64_t* d_costs, int n, long long c);
 // cost model of the triple product rows (see spgemm_b200_row_costs)
 cudaError_t launch_triple_costs(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool upper_only,
-                                int np, int panel_w, int64_t* d_costs);
+                                bool q_runs, int np, int panel_w, int64_t* d_costs);
 
 // ---- spgemm_sparse.cu ---------------------------------------------------------------------------
 struct SparseJob {

@@ -122,7 +122,7 @@ void worker(Job* job, int d) {
         std::vector<int64_t> costs((size_t)m);
         rc = dalloc(&d_costs, (size_t)m);
         if (!rc) rc = row_costs_impl(a, job->kind == K_TRIPLE ? ht : b, job->kind == K_TRIPLE ? b : nullptr,
-                                     job->upper_only, d_costs);
+                                     job->upper_only, job->kind == K_DENSE ? job->b.cols : 0, d_costs);
         if (!rc && m > 0) {
             cudaError_t e = cudaMemcpyAsync(costs.data(), d_costs, (size_t)m * 8, cudaMemcpyDeviceToHost, g.stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
@@ -143,23 +143,26 @@ void worker(Job* job, int d) {
             rc = csr_impl(a, b, job->upper_only, r0, r1, &part);
             if (!rc) job->res->parts[d] = part;
             mark(EV_POST); mark(EV_D2H);
-        } else if (r1 > r0) {
-            if (job->kind != K_TRIPLE) mark(EV_SYMBOLIC);
-            rc = dalloc(&d_c, (size_t)(r1 - r0) * (size_t)n);
-            if (!rc && job->kind == K_TRIPLE) {
-                rc = dalloc(&d_cnt, 4);
-                if (!rc) rc = triple_rows(a, b, nullptr, job->upper_only, r0, r1, d_c, d_cnt);
-            } else if (!rc) {
-                rc = dense_rows(a, b, job->upper_only, r0, r1, d_c);
+        } else {
+            const bool square = job->kind == K_TRIPLE || job->a.rows == job->b.cols;
+            if (r1 > r0) {
+                if (job->kind != K_TRIPLE) mark(EV_SYMBOLIC);
+                rc = dalloc(&d_c, (size_t)(r1 - r0) * (size_t)n);
+                if (!rc && job->kind == K_TRIPLE) {
+                    rc = dalloc(&d_cnt, 4);
+                    if (!rc) rc = triple_rows(a, b, nullptr, job->upper_only, r0, r1, d_c, d_cnt);
+                } else if (!rc) {
+                    rc = dense_rows(a, b, job->upper_only, r0, r1, d_c);
+                }
+                mark(EV_NUMERIC); mark(EV_POST);
             }
-            mark(EV_NUMERIC); mark(EV_POST);
             if (!rc) {
                 NvtxRange nv("spgemm_b200:multi:d2h");
-                cudaError_t e;
-                const bool square = job->kind == K_TRIPLE || job->a.rows == job->b.cols;
+                cudaError_t e = cudaSuccess;
                 if (job->upper_only && square) {
-                    e = d2h_upper_rows(d_c, n, r0, r1, job->c_host);
-                } else {
+                    // every worker zeroes its share of the lower triangle, whether or not it owns rows
+                    e = d2h_upper_rows(d_c, n, r0, r1, job->c_host, d, job->n_gpus);
+                } else if (r1 > r0) {
                     e = cudaMemcpyAsync(job->c_host + (size_t)r0 * n, d_c, (size_t)(r1 - r0) * n * 8,
                                         cudaMemcpyDeviceToHost, g.stream);
                     g.stats.bytes_d2h += (int64_t)(r1 - r0) * n * 8;

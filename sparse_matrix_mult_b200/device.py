@@ -254,13 +254,14 @@ def symmetrize(out, n):
     _check(matrix_ops.get_lib().spgemm_b200_symmetrize_dev(_vp(ptr), int(n)), "spgemm_b200_symmetrize_dev")
 
 
-def row_costs(a, b, q=None, upper_only=False):
-    """(device buffer of int64 per-row costs, total).  Sparse/dense: a=A, b=B.  Triple: a=H, b=H^T, q=Q."""
+def row_costs(a, b, q=None, upper_only=False, dense_cols=0):
+    """(device buffer of int64 per-row costs, total).  Sparse/dense: a=A, b=B (dense_cols = columns of a dense output
+    row, 0 for sparse output).  Triple: a=H, b=H^T, q=Q."""
     lib = matrix_ops.get_lib()
     d = lib.spgemm_b200_device_alloc(max(1, a.shape[0]) * 8)
     total = ctypes.c_int64(0)
-    _check(lib.spgemm_b200_row_costs(a._h, b._h, q._h if q is not None else None, int(bool(upper_only)), _vp(d),
-                                     ctypes.byref(total)), "spgemm_b200_row_costs")
+    _check(lib.spgemm_b200_row_costs(a._h, b._h, q._h if q is not None else None, int(bool(upper_only)), int(dense_cols),
+                                     _vp(d), ctypes.byref(total)), "spgemm_b200_row_costs")
     return d, int(total.value)
 
 

@@ -241,7 +241,7 @@ def cuda_partition(a_t, b_t, kind, upper_only, world):
         Ht = A.transpose()
         costs, _ = dev.row_costs(A, Ht, B, upper_only)
     else:
-        costs, _ = dev.row_costs(A, B, None, upper_only)
+        costs, _ = dev.row_costs(A, B, None, upper_only, dense_cols=(b_t[0][1] if kind == "dense" else 0))
     bounds = dev.partition_rows(costs, a_t[0][0], world)
     matrix_ops.get_lib().spgemm_b200_device_free(costs)
     return bounds.astype(np.int64)

@@ -109,7 +109,7 @@ class MatrixOpsLibrary:
         L.spgemm_b200_triple_dev.argtypes = [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
         L.spgemm_b200_mirror_dev.argtypes = [_vp, ctypes.c_int]
         L.spgemm_b200_symmetrize_dev.argtypes = [_vp, ctypes.c_int]
-        L.spgemm_b200_row_costs.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int64)]
+        L.spgemm_b200_row_costs.argtypes = [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int64)]
         L.spgemm_b200_partition.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _i32p]
         L.spgemm_b200_device_alloc.argtypes = [ctypes.c_size_t]
         L.spgemm_b200_device_alloc.restype = _vp
