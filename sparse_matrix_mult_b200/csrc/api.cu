@@ -332,12 +332,8 @@ void host_cache_clear() {
 
 // ===================================================================================================
 // operands
-int upload(int rows, int cols, const int32_t* ptr, const int32_t* idx, const double* val, spgemm_b200_mat** out) {
+int alloc_mat(int rows, int cols, int64_t nnz, spgemm_b200_mat** out) {
     Ctx& g = cx();
-    const int64_t nnz = rows > 0 ? (int64_t)ptr[rows] - ptr[0] : 0;
-    if (nnz < 0) return fail(SPGEMM_B200_ERR_ARG, "indptr is not non-decreasing");
-    if (nnz > 0 && (!idx || !val)) return fail(SPGEMM_B200_ERR_ARG, "null indices/values with nnz > 0");
-    if (rows > 0 && ptr[0] != 0) return fail(SPGEMM_B200_ERR_ARG, "indptr[0] must be 0");
     spgemm_b200_mat* m = new spgemm_b200_mat{rows, cols, nnz, nullptr, nullptr, nullptr, true, g.device,
                                              nullptr, false, false, false, false, false, nullptr};
     int rc;
@@ -346,6 +342,19 @@ int upload(int rows, int cols, const int32_t* ptr, const int32_t* idx, const dou
         mat_release(m);
         return rc;
     }
+    *out = m;
+    return SPGEMM_B200_OK;
+}
+
+int upload(int rows, int cols, const int32_t* ptr, const int32_t* idx, const double* val, spgemm_b200_mat** out) {
+    Ctx& g = cx();
+    const int64_t nnz = rows > 0 ? (int64_t)ptr[rows] - ptr[0] : 0;
+    if (nnz < 0) return fail(SPGEMM_B200_ERR_ARG, "indptr is not non-decreasing");
+    if (nnz > 0 && (!idx || !val)) return fail(SPGEMM_B200_ERR_ARG, "null indices/values with nnz > 0");
+    if (rows > 0 && ptr[0] != 0) return fail(SPGEMM_B200_ERR_ARG, "indptr[0] must be 0");
+    spgemm_b200_mat* m = nullptr;
+    int rc = alloc_mat(rows, cols, nnz, &m);
+    if (rc) return rc;
     cudaError_t e = cudaSuccess;
     if (rows > 0) e = cudaMemcpyAsync(m->ptr, ptr, ((size_t)rows + 1) * 4, cudaMemcpyHostToDevice, g.stream);
     else e = cudaMemsetAsync(m->ptr, 0, 4, g.stream);

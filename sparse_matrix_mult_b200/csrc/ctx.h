@@ -116,6 +116,7 @@ void finish_stats();
 
 // ---- building blocks (all run on cx()) ----------------------------------------------------------------
 int upload(int rows, int cols, const int32_t* ptr, const int32_t* idx, const double* val, spgemm_b200_mat** out);
+int alloc_mat(int rows, int cols, int64_t nnz, spgemm_b200_mat** out);   // device arrays only, nothing copied
 void mat_release(spgemm_b200_mat* m);             // frees device arrays on cx() and deletes the handle
 void result_release(spgemm_b200_result* r);
 int transpose_impl(const spgemm_b200_mat* x, spgemm_b200_mat** out, bool sort_desc);

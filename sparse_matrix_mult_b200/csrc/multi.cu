@@ -5,7 +5,9 @@
 // one host thread per GPU inside the call, each with its own context (stream, pool), and a contiguous row range
 // from the flop-balanced partition.  The path shards by output rows with no exchange between shards, so there
 // is no collective in the data path:
-//     every GPU : H2D of the operands over ITS OWN PCIe link (in parallel) -> checks (-> H^T)
+//     every GPU : H2D of 1/N of every operand array over ITS OWN PCIe link, then the other N-1 parts from its peers
+//                 over NVLink (peer copies: a scatter + all-gather, so the host is read once instead of N times;
+//                 whole-operand uploads per GPU when the devices cannot reach each other) -> checks (-> H^T)
 //     GPU 0     : per-row cost pass -> partition (published to the others through a barrier)
 //     every GPU : its row block with the same kernels as the single-GPU path
 //                 -> D2H of its block straight into its rows of the caller's result (N PCIe links at once;
@@ -63,9 +65,16 @@ struct Operand {
     const double* val;
 };
 
+struct Shard {                    // what a worker publishes for the peer all-gather of the operands
+    void* base[2][3] = {};        // [operand][ptr, idx, val] device arrays
+    cudaEvent_t ready = nullptr;  // its own slices have landed
+};
+
 struct Job {
     Kind kind;
     int n_gpus;
+    bool peers = false;           // every GPU can read every other GPU's memory
+    std::vector<Shard> shards;
     Operand a, b;                 // dense/csr: A, B;  triple: H, Q
     int upper_only;
     double* c_host = nullptr;     // dense / triple
@@ -76,7 +85,7 @@ struct Job {
     int status = SPGEMM_B200_OK;
     std::string err;
     std::vector<spgemm_b200_stats> stats;
-    Job(int n) : n_gpus(n), bounds(n + 1, 0), bar(n), stats(n) {}
+    Job(int n) : n_gpus(n), shards(n), bounds(n + 1, 0), bar(n), stats(n) {}
     void set_error(int code) {
         std::lock_guard<std::mutex> lk(mu);
         if (status == SPGEMM_B200_OK) { status = code; err = spgemm_b200_last_error(); }
@@ -91,11 +100,91 @@ std::mutex g_multi_mu;                         // one multi-GPU call at a time
 std::vector<int32_t> g_last_bounds;
 std::vector<spgemm_b200_stats> g_last_stats;
 
-// Every worker reaches both barriers whatever happens (a worker that failed just stops doing work).
+// Peer access between the first n devices (both the driver-level switch and the access list of the private pools),
+// set up once per process.  False when some pair cannot reach each other.
+bool ensure_peers(int n) {
+    static std::mutex mu;
+    static int have = 0;          // peers are set up among devices [0, have)
+    static bool ok = true;
+    std::lock_guard<std::mutex> lk(mu);
+    if (n <= have) return ok;
+    for (int d = 0; d < n && ok; ++d) {
+        Ctx* c = device_ctx(d);
+        if (!c) { ok = false; break; }
+        CallGuard guard(c);
+        for (int p = 0; p < n; ++p) {
+            if (p == d) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, d, p) != cudaSuccess || !can) { ok = false; break; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(p, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+            cudaMemAccessDesc desc = {};
+            desc.location.type = cudaMemLocationTypeDevice;
+            desc.location.id = p;
+            desc.flags = cudaMemAccessFlagsProtReadWrite;
+            if (cudaMemPoolSetAccess(c->pool, &desc, 1) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        }
+    }
+    have = n;
+    return ok;
+}
+
+// This worker's 1/N slice of every operand array, host -> its own device (scatter half of the operand broadcast).
+int upload_slices(Job* job, int d, const Operand& op, int which, spgemm_b200_mat** out) {
+    Ctx& g = cx();
+    const int64_t nnz = op.rows > 0 ? (int64_t)op.ptr[op.rows] - op.ptr[0] : 0;
+    if (nnz < 0 || (op.rows > 0 && op.ptr[0] != 0)) return fail(SPGEMM_B200_ERR_ARG, "multi: bad indptr");
+    if (nnz > 0 && (!op.idx || !op.val)) return fail(SPGEMM_B200_ERR_ARG, "multi: null indices/values with nnz > 0");
+    spgemm_b200_mat* m = nullptr;
+    int rc = alloc_mat(op.rows, op.cols, nnz, &m);
+    if (rc) return rc;
+    const void* host[3] = {op.ptr, op.idx, op.val};
+    void* dev[3] = {m->ptr, m->idx, m->val};
+    const size_t count[3] = {(size_t)op.rows + 1, (size_t)nnz, (size_t)nnz}, width[3] = {4, 4, 8};
+    const int N = job->n_gpus;
+    for (int k = 0; k < 3; ++k) {
+        const size_t lo = count[k] * d / N, hi = count[k] * (d + 1) / N;
+        job->shards[d].base[which][k] = dev[k];
+        if (hi > lo) {
+            cudaError_t e = cudaMemcpyAsync((char*)dev[k] + lo * width[k], (const char*)host[k] + lo * width[k],
+                                            (hi - lo) * width[k], cudaMemcpyHostToDevice, g.stream);
+            if (e != cudaSuccess) { mat_release(m); return fail(SPGEMM_B200_ERR_CUDA, "multi: slice upload", e); }
+            g.stats.bytes_h2d += (int64_t)((hi - lo) * width[k]);
+        }
+    }
+    *out = m;
+    return SPGEMM_B200_OK;
+}
+
+// The other N-1 slices of an operand from the peers that uploaded them (all-gather half, NVLink).
+int gather_slices(Job* job, int d, const spgemm_b200_mat* m, int which) {
+    Ctx& g = cx();
+    void* dev[3] = {m->ptr, m->idx, m->val};
+    const size_t count[3] = {(size_t)m->rows + 1, (size_t)m->nnz, (size_t)m->nnz}, width[3] = {4, 4, 8};
+    const int N = job->n_gpus;
+    for (int step = 1; step < N; ++step) {
+        const int s = (d + step) % N;                 // every worker starts at a different peer
+        for (int k = 0; k < 3; ++k) {
+            const size_t lo = count[k] * s / N, hi = count[k] * (s + 1) / N;
+            if (hi <= lo) continue;
+            CU(cudaMemcpyPeerAsync((char*)dev[k] + lo * width[k], d, (const char*)job->shards[s].base[which][k] + lo * width[k],
+                                   s, (hi - lo) * width[k], g.stream));
+        }
+    }
+    return SPGEMM_B200_OK;
+}
+
+// Every worker reaches every barrier whatever happens (a worker that failed just stops doing work).
 void worker(Job* job, int d) {
     int rc = SPGEMM_B200_OK;
     Ctx* c = device_ctx(d);
-    if (!c) { job->set_error(SPGEMM_B200_ERR_CUDA); job->bar.wait(); job->bar.wait(); return; }
+    if (!c) {
+        job->set_error(SPGEMM_B200_ERR_CUDA);
+        if (job->peers) job->bar.wait();
+        job->bar.wait(); job->bar.wait();
+        return;
+    }
     CallGuard guard(c);
     Ctx& g = cx();
     begin_call();
@@ -107,7 +196,30 @@ void worker(Job* job, int d) {
                       job->a.val == job->b.val && job->a.rows == job->b.rows && job->a.cols == job->b.cols;
     const int m = job->a.rows;
     // ---- phase 1: operands in, checks, H^T, (GPU 0) partition ----
-    {
+    if (job->peers) {
+        NvtxRange nv("spgemm_b200:multi:scatter+allgather");
+        rc = upload_slices(job, d, job->a, 0, &a);
+        if (!rc) {
+            if (same) b = a;
+            else rc = upload_slices(job, d, job->b, 1, &b);
+        }
+        cudaError_t e = cudaSuccess;
+        if (!rc) e = cudaEventCreateWithFlags(&job->shards[d].ready, cudaEventDisableTiming);
+        if (!rc && e == cudaSuccess) e = cudaEventRecord(job->shards[d].ready, g.stream);
+        if (!rc && e != cudaSuccess) rc = fail(SPGEMM_B200_ERR_CUDA, "multi: slice event", e);
+        if (rc) job->set_error(rc);
+        job->bar.wait();                                   // every worker's arrays and event are published
+        if (!job->failed()) {
+            for (int s = 0; s < job->n_gpus && !rc; ++s)
+                if (s != d && cudaStreamWaitEvent(g.stream, job->shards[s].ready, 0) != cudaSuccess)
+                    rc = fail(SPGEMM_B200_ERR_CUDA, "multi: wait for a peer's slices");
+            if (!rc) rc = gather_slices(job, d, a, 0);
+            if (!rc && b != a) rc = gather_slices(job, d, b, 1);
+        } else if (!rc) {
+            rc = SPGEMM_B200_ERR_STATE;                   // another worker failed: skip the work, keep the barriers
+        }
+        mark(EV_H2D);
+    } else {
         NvtxRange nv("spgemm_b200:multi:h2d");
         rc = upload(job->a.rows, job->a.cols, job->a.ptr, job->a.idx, job->a.val, &a);
         if (!rc) {
@@ -185,10 +297,13 @@ void worker(Job* job, int d) {
     mat_release(a);
     mat_release(ht);
     job->bar.wait();
+    if (job->shards[d].ready) cudaEventDestroy(job->shards[d].ready);
 }
 
 int run(Job& job) {
     std::lock_guard<std::mutex> lk(g_multi_mu);
+    const char* no_peer = getenv("SPGEMM_B200_MULTI_NO_PEER");     // experiments: whole-operand upload on every GPU
+    job.peers = job.n_gpus > 1 && !(no_peer && atoi(no_peer)) && ensure_peers(job.n_gpus);
     std::vector<std::thread> threads;
     for (int d = 1; d < job.n_gpus; ++d) threads.emplace_back(worker, &job, d);
     worker(&job, 0);
