@@ -518,7 +518,7 @@ static void zero_nt(double* p, size_t count) {
 // columns [gG, n) as one 2-D copy and has columns [0, gG) zeroed on the host.  Halves the bytes on the link.
 // The zero fill is work any thread can do whoever owns the rows: share `part` of `nparts` (the multi-GPU driver
 // passes its GPU's index so the lower triangle is split evenly over all workers; one GPU: 0 of 1) takes the blocks
-// g = part (mod nparts), on `SPGEMM_B200_ZERO_THREADS` threads (default: the host's cores / nparts, at most 4).
+// g = part (mod nparts), on `SPGEMM_B200_ZERO_THREADS` threads (default: the host's cores / nparts, at most 8).
 // d_c holds rows [r0, r1) only; c_host is the full n-column host matrix.
 constexpr int kUpperBlocks = 256;
 
@@ -535,11 +535,13 @@ cudaError_t d2h_upper_rows(const double* d_c, int n, int r0, int r1, double* c_h
         g.stats.bytes_d2h += (int64_t)(n - b0) * (s1 - s0) * 8;
     }
     // zero this share of the lower-left rectangles on the host meanwhile
-    // (measured on a 16-core host, cfg 5, one GPU: the copy alone takes 123 ms; with 4 / 8 / 16 / 32 zeroing threads
-    //  beside it 142 / 158 / 150 / 139 ms -- more threads only fight the DMA for memory bandwidth)
+    // (measured, cfg 5: the copy alone takes 123 ms on one GPU -- PCIe at 52 GB/s; with 2 / 4 / 8 / 16 zeroing threads
+    //  beside it 143 / 142 / 138 / 138 ms on a 32-core host.  On 2 - 8 GPUs the copy + zero fill takes ~105 ms whatever
+    //  the thread count: 12.8 GB written into host memory at ~120 GB/s, the host's memory write bandwidth --
+    //  profiles/r2/multi_gpu.md)
     unsigned hw = std::thread::hardware_concurrency();
     int nthreads = hw == 0 ? 4 : (int)hw / (nparts > 0 ? nparts : 1);
-    if (nthreads > 4) nthreads = 4;
+    if (nthreads > 8) nthreads = 8;
     if (nthreads < 1) nthreads = 1;
     if (const char* ev = getenv("SPGEMM_B200_ZERO_THREADS")) nthreads = atoi(ev);      // 0 = skip (experiments only)
     if ((size_t)n * n < ((size_t)1 << 22) && nthreads > 1) nthreads = 1;
