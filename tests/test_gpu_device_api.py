@@ -289,3 +289,63 @@ def test_trim_releases_cached_memory():
     sparse_matrix_multiply(a, b, output_format='dense')
     assert matrix_ops.get_lib().spgemm_b200_trim(0) == 0
     assert_dense_equal(sparse_matrix_multiply(a, b, output_format='dense'), port.spgemm_dense(a, b), "after trim")
+
+
+# ---- triple product: column panels and both kernels at sizes the oracle checks in full -------------------------
+@pytest.mark.parametrize("panels", [1, 2, 3, 5])
+@pytest.mark.parametrize("generic", [0, 1])
+def test_triple_panels_forced(panels, generic, monkeypatch):
+    """The default plan only cuts C into several column panels for outputs wider than the shared-memory segment or
+    an H^T beyond the L2 budget (cfg 5); here the panel count is forced so that the multi-panel bookkeeping -- which
+    panel holds a row's diagonal, who writes the zeros left of it, the (panel, row) ticket order -- runs on small
+    inputs, with the lean kernel for banded Q (rows of Q are runs of consecutive columns) and with the general one."""
+    monkeypatch.setenv("SPGEMM_B200_TRIPLE_PANELS", str(panels))
+    monkeypatch.setenv("SPGEMM_B200_TRIPLE_GENERIC", str(generic))
+    for name in ("cfg3s", "cfg5s"):
+        w = synthetic.workload(name)
+        h, q = w["a"], w["b"]
+        assert_dense_equal(sparse_matrix_multiply(h, q, use_triple_product=True), port.triple_product(h, q, 0),
+                           f"{name} panels={panels} generic={generic} upper")
+        assert_dense_equal(sparse_matrix_multiply(h, q, use_triple_product=True, compute_full_matrix=1),
+                           port.triple_product(h, q, 1), f"{name} panels={panels} generic={generic} reference-full")
+    # row ranges that start inside a panel, through the device API
+    w = synthetic.workload("cfg3s")
+    h, q = w["a"], w["b"]
+    H, Q = dev.DeviceMatrix.from_scipy(h), dev.DeviceMatrix.from_scipy(q)
+    want = port.triple_product(h, q, 0)
+    for r0, r1 in [(0, 37), (37, 250), (250, 400)]:
+        out = dev.triple_product(H, Q, None, True, r0, r1)
+        np.testing.assert_allclose(out.to_host(), want[r0:r1], rtol=1e-12, atol=1e-14)
+        out.free()
+
+
+def test_triple_q_with_wide_and_ragged_runs():
+    """Banded Q whose runs are longer than one pass of the weight table (96 columns), ragged at the matrix edges, next
+    to an H with empty rows and a duplicate column entry."""
+    rng = np.random.default_rng(4)
+    n, k = 300, 2500
+    h = sp.random(n, k, density=0.01, format='csr', random_state=rng).tolil()
+    h[5, :] = 0
+    h[17, :] = 0
+    h = h.tocsr()
+    h.eliminate_zeros()
+    # duplicate entry: row 3 names its first column twice (CSR inputs are used as they are)
+    s, e = h.indptr[3], h.indptr[4]
+    if e - s >= 2:
+        h.indices[s + 1] = h.indices[s]
+    q = synthetic.banded_cov(k, half_width=120, length=30.0)          # runs of up to 241 columns
+    got = sparse_matrix_multiply(h, q, use_triple_product=True)
+    assert_dense_equal(got, port.triple_product(h, q, 0), "wide runs")
+    # a Q that is sorted but not made of runs takes the general kernel
+    q2 = sp.random(k, k, density=0.004, format='csr', random_state=rng)
+    assert_dense_equal(sparse_matrix_multiply(h, q2, use_triple_product=True), port.triple_product(h, q2, 0), "general Q")
+
+
+def test_multi_gpu_without_peer_copies(monkeypatch):
+    """The whole-operand upload path of the multi-GPU driver (taken when the GPUs cannot reach each other)."""
+    monkeypatch.setenv("SPGEMM_B200_FORCE_MULTI", "1")
+    monkeypatch.setenv("SPGEMM_B200_MULTI_NO_PEER", "1")
+    w = synthetic.workload("cfg3s")
+    want = port.sparse_matrix_multiply(w["a"], w["b"], **w["kwargs"])
+    for n_gpus in _gpu_counts():
+        assert_dense_equal(sparse_matrix_multiply(w["a"], w["b"], n_gpus=n_gpus, **w["kwargs"]), want, f"no-peer n_gpus={n_gpus}")
