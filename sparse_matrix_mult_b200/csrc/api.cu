@@ -632,33 +632,59 @@ int csr_impl(spgemm_b200_mat* a, spgemm_b200_mat* b_in, int upper_only, int r0, 
     memcpy(&total_products, h + 24, 8);
     g.stats.products = (int64_t)total_products;
 
+    // Heavy rows: the symbolic phase keeps their column bitmaps (up to SPGEMM_B200_BITMAP_KEEP_MB, default 4096) so the
+    // numeric rank kernel does not rebuild them.  One slot per row of the bitmap bin while they last.
+    SavedBitmaps saved{nullptr, nullptr, d_work + 4, 0, saved_bitmap_words(n)};
+    int32_t* d_slot_of_row = nullptr;
+    if (sym_counts[SYM_BITMAP] > 0) {
+        const char* kv = getenv("SPGEMM_B200_BITMAP_KEEP_MB");
+        const int64_t budget = (int64_t)(kv ? atoll(kv) : 4096) << 20;
+        int64_t slots = budget / ((int64_t)saved.words * 4);
+        if (slots > sym_counts[SYM_BITMAP]) slots = sym_counts[SYM_BITMAP];
+        if (slots > 0 && dalloc(&d_slot_of_row, (size_t)m) == SPGEMM_B200_OK) {
+            if (dalloc(&saved.bits, (size_t)slots * saved.words) == SPGEMM_B200_OK) {
+                saved.slots = (int)slots;
+                saved.slot_of_row = d_slot_of_row;
+                e = cudaMemsetAsync(d_slot_of_row, 0xff, (size_t)m * 4, g.stream);
+                if (e != cudaSuccess) return bail(fail(SPGEMM_B200_ERR_CUDA, "bitmap slots", e));
+            } else {
+                cudaGetLastError();                            // no room: the numeric phase rebuilds the bitmaps
+                saved.bits = nullptr;
+            }
+        }
+    }
+    auto bail2 = [&](int code) {
+        dfree(saved.bits); dfree(d_slot_of_row);
+        return bail(code);
+    };
     {
         NvtxRange nv("spgemm_b200:symbolic");
-        e = launch_symbolic(lc, job, d_lists, sym_counts, d_nnz, d_work);
+        e = launch_symbolic(lc, job, d_lists, sym_counts, d_nnz, d_work, saved);
         if (e == cudaSuccess) e = launch_scan_i64(lc, d_nnz, res->d_ptr, m, scan_tmp);
         if (e == cudaSuccess) e = cudaMemsetAsync(d_cursor, 0, 16 * sizeof(int32_t), g.stream);
         if (e == cudaSuccess) e = launch_bin_by_nnz(lc, d_nnz, m, d_lists, d_cursor);
-        if (e != cudaSuccess) return bail(fail(SPGEMM_B200_ERR_CUDA, "symbolic phase", e));
+        if (e != cudaSuccess) return bail2(fail(SPGEMM_B200_ERR_CUDA, "symbolic phase", e));
         mark(EV_SYMBOLIC);
     }
     int64_t* h64 = reinterpret_cast<int64_t*>(h + 32);
     e = cudaMemcpyAsync(h, d_cursor, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, g.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h64, res->d_ptr + m, 8, cudaMemcpyDeviceToHost, g.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
-    if (e != cudaSuccess) return bail(fail(SPGEMM_B200_ERR_CUDA, "nnz(C)", e));
+    if (e != cudaSuccess) return bail2(fail(SPGEMM_B200_ERR_CUDA, "nnz(C)", e));
     int32_t num_counts[NUM_BINS];
     for (int k = 0; k < NUM_BINS; ++k) num_counts[k] = h[k];
     res->nnz = *h64;
     g.stats.nnz_c = res->nnz;
     // bytes(A) + bytes(B) + bytes(C); a row slice of A is charged pro rata
     g.stats.bytes_min = csr_bytes(m, a->rows ? a->nnz * m / a->rows : 0) + csr_bytes(b->rows, b->nnz) + csr_bytes(m, res->nnz);
-    if ((rc = dalloc(&res->d_idx, (size_t)res->nnz)) || (rc = dalloc(&res->d_val, (size_t)res->nnz))) return bail(rc);
+    if ((rc = dalloc(&res->d_idx, (size_t)res->nnz)) || (rc = dalloc(&res->d_val, (size_t)res->nnz))) return bail2(rc);
     {
         NvtxRange nv("spgemm_b200:numeric");
-        e = launch_numeric(lc, job, d_lists, num_counts, res->d_ptr, res->d_idx, res->d_val, d_work);
-        if (e != cudaSuccess) return bail(fail(SPGEMM_B200_ERR_CUDA, "numeric phase", e));
+        e = launch_numeric(lc, job, d_lists, num_counts, res->d_ptr, res->d_idx, res->d_val, d_work, saved);
+        if (e != cudaSuccess) return bail2(fail(SPGEMM_B200_ERR_CUDA, "numeric phase", e));
         mark(EV_NUMERIC);
     }
+    dfree(saved.bits); dfree(d_slot_of_row);
     dfree(ws); dfree(scan_tmp);
     *out = res;
     return SPGEMM_B200_OK;

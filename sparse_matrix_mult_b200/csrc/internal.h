@@ -80,11 +80,21 @@ struct SparseJob {
     bool upper_only;
     const int32_t* d_b_sorted;   // device flag
 };
+// Column bitmaps of heavy rows handed from the symbolic to the numeric phase (so the numeric rank kernel does not
+// rebuild them with one more pass over the row's products).  bits == nullptr: nothing is kept.
+struct SavedBitmaps {
+    unsigned* bits;            // slots * words
+    int32_t* slot_of_row;      // [nrows], -1 = not kept (preset by the caller)
+    int32_t* counter;          // next free slot (zeroed by the caller)
+    int slots, words;
+};
+int saved_bitmap_words(int cols);
 cudaError_t launch_symbolic(const LaunchCtx& lc, const SparseJob& job, const int32_t* d_lists,
-                            const int32_t* h_counts /* host, SYM_BINS */, int32_t* d_nnz, int32_t* d_work_counter);
+                            const int32_t* h_counts /* host, SYM_BINS */, int32_t* d_nnz, int32_t* d_work_counter,
+                            const SavedBitmaps& saved);
 cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int32_t* d_lists,
                            const int32_t* h_counts /* host, NUM_BINS */, const int64_t* c_ptr, int32_t* c_idx,
-                           double* c_val, int32_t* d_work_counter);
+                           double* c_val, int32_t* d_work_counter, const SavedBitmaps& saved);
 cudaError_t sparse_kernels_configure();
 
 // ---- spgemm_dense.cu ----------------------------------------------------------------------------

@@ -106,13 +106,17 @@ k_symbolic_warp(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __re
 }
 
 // Symbolic, block per row, occupancy bitmap over column windows of `window_bits` columns.
+// When the whole row fits one window and `saved` is given, the finished bitmap is also stored to global memory
+// (saved.words words per slot, slots handed out by an atomic counter until they run out; saved.slot_of_row[r] = the
+// slot or -1): the numeric rank kernel then loads it instead of rebuilding it with a second pass over the products.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_symbolic_bitmap(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __restrict__ b_sorted_flag,
                   const int32_t* __restrict__ list, int count, int window_bits, int32_t* __restrict__ nnz,
-                  int32_t* __restrict__ work_counter) {
+                  int32_t* __restrict__ work_counter, SavedBitmaps saved) {
     extern __shared__ unsigned s_bits[];
     __shared__ int s_item;
+    __shared__ int s_slot;
     __shared__ int s_red[33];
     __shared__ SegScratch<THREADS> s_seg;
     const bool b_sorted = *b_sorted_flag != 0;
@@ -144,6 +148,19 @@ k_symbolic_bitmap(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __
             int sum;
             block_excl_scan<int>(cnt, s_red, &sum);
             total += sum;
+            if (saved.bits != nullptr && window_bits >= n) {       // single window: keep the bitmap for the numeric phase
+                if (threadIdx.x == 0) {
+                    const int slot = sum > kWarpCap1K ? atomicAdd(saved.counter, 1) : saved.slots;   // warp-bin rows: no
+                    s_slot = slot < saved.slots ? slot : -1;
+                    saved.slot_of_row[r] = s_slot;
+                }
+                __syncthreads();
+                if (s_slot >= 0) {
+                    unsigned* dst = saved.bits + (size_t)s_slot * saved.words;
+                    for (int t = threadIdx.x; t < saved.words; t += blockDim.x) dst[t] = t < words ? s_bits[t] : 0u;
+                }
+                __syncthreads();
+            }
         }
         if (threadIdx.x == 0) nnz[r] = total;
     }
@@ -244,7 +261,7 @@ __global__ void __launch_bounds__(THREADS)
 k_numeric_rank(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __restrict__ b_sorted_flag,
                const int32_t* __restrict__ list, int count, int stride, int window,
                const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, double* __restrict__ c_val,
-               int32_t* __restrict__ work_counter) {
+               int32_t* __restrict__ work_counter, SavedBitmaps saved) {
     extern __shared__ unsigned s_dynu[];
     RankTable<COMPACT> tab;
     tab.bits = s_dynu;
@@ -267,21 +284,30 @@ k_numeric_rank(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __res
         const int a_begin = __ldg(A.ptr + i), a_end = __ldg(A.ptr + i + 1);
         const int lo = upper_only ? i : 0;
         int64_t out = __ldg(c_ptr + r);
+        // the symbolic phase may have kept this row's bitmap (single-window rows only)
+        const int slot = (saved.bits != nullptr && window >= n) ? __ldg(saved.slot_of_row + r) : -1;
         for (int w0 = (lo / window) * window; w0 < n; w0 += window) {
             const int wl = max(w0, lo), wh = min(w0 + window, n);
             const int words = (((wh - w0 + 31) >> 5) + 3) & ~3;            // multiple of 4 (window is one of 128)
             const bool col_windowed = upper_only || window < n;
-            if (COMPACT) for (int t = threadIdx.x; t < words; t += THREADS) tab.bits[t] = 0u;
-            else for (int t = threadIdx.x; t < words; t += THREADS) reinterpret_cast<uint2*>(tab.bits)[t] = make_uint2(0u, 0u);
-            __syncthreads();
-            // pass 1: occupancy
-            expand_row_block<false>(A, B, a_begin, a_end, wl, wh, col_windowed, b_sorted, s_seg, [&](int c, double) {
-                const int o = c - w0;
-                const unsigned m = 1u << (o & 31);
-                unsigned* wp = tab.word_ptr(o >> 5);
-                if (!(*((volatile unsigned*)wp) & m)) atomicOr(wp, m);
-            });
-            __syncthreads();
+            if (slot >= 0) {
+                const unsigned* src = saved.bits + (size_t)slot * saved.words;
+                if (COMPACT) for (int t = threadIdx.x; t < words; t += THREADS) tab.bits[t] = __ldg(src + t);
+                else for (int t = threadIdx.x; t < words; t += THREADS) reinterpret_cast<uint2*>(tab.bits)[t] = make_uint2(__ldg(src + t), 0u);
+                __syncthreads();
+            } else {
+                if (COMPACT) for (int t = threadIdx.x; t < words; t += THREADS) tab.bits[t] = 0u;
+                else for (int t = threadIdx.x; t < words; t += THREADS) reinterpret_cast<uint2*>(tab.bits)[t] = make_uint2(0u, 0u);
+                __syncthreads();
+                // pass 1: occupancy
+                expand_row_block<false>(A, B, a_begin, a_end, wl, wh, col_windowed, b_sorted, s_seg, [&](int c, double) {
+                    const int o = c - w0;
+                    const unsigned m = 1u << (o & 31);
+                    unsigned* wp = tab.word_ptr(o >> 5);
+                    if (!(*((volatile unsigned*)wp) & m)) atomicOr(wp, m);
+                });
+                __syncthreads();
+            }
             // exclusive popcount prefix (per word, or per group of four words)
             const int units = COMPACT ? words >> 2 : words;
             int nnz_w = 0;
@@ -379,7 +405,7 @@ static inline int grid_for(int items, int per_block, int cap) {
 }
 
 cudaError_t launch_symbolic(const LaunchCtx& lc, const SparseJob& job, const int32_t* d_lists, const int32_t* h_counts,
-                            int32_t* d_nnz, int32_t* d_work_counter) {
+                            int32_t* d_nnz, int32_t* d_work_counter, const SavedBitmaps& saved) {
     const int up = job.upper_only ? 1 : 0;
     const size_t stride = (size_t)job.nrows;
     const int cap = lc.sm_count * 16;
@@ -422,19 +448,25 @@ cudaError_t launch_symbolic(const LaunchCtx& lc, const SparseJob& job, const int
         if (per_sm >= 2)
             k_symbolic_bitmap<512><<<grid_for(h_counts[SYM_BITMAP], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
                 job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + SYM_BITMAP * stride, h_counts[SYM_BITMAP],
-                (int)window_bits, d_nnz, d_work_counter);
+                (int)window_bits, d_nnz, d_work_counter, saved);
         else                                           // one block per SM: make it a full 1024 threads
             k_symbolic_bitmap<1024><<<grid_for(h_counts[SYM_BITMAP], 1, lc.sm_count), 1024, smem, lc.stream>>>(
                 job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + SYM_BITMAP * stride, h_counts[SYM_BITMAP],
-                (int)window_bits, d_nnz, d_work_counter);
+                (int)window_bits, d_nnz, d_work_counter, saved);
         SB_LAUNCH_CHECK(lc);
     }
     fork.join();
     return cudaSuccess;
 }
 
+// words of one saved bitmap: the numeric kernel's rounding of the column count (a multiple of 4 words)
+int saved_bitmap_words(int cols) {
+    return (int)((((int64_t)cols + 127) & ~(int64_t)127) >> 5);
+}
+
 cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int32_t* d_lists, const int32_t* h_counts,
-                           const int64_t* c_ptr, int32_t* c_idx, double* c_val, int32_t* d_work_counter) {
+                           const int64_t* c_ptr, int32_t* c_idx, double* c_val, int32_t* d_work_counter,
+                           const SavedBitmaps& saved) {
     const int up = job.upper_only ? 1 : 0;
     const size_t stride = (size_t)job.nrows;
     const int cap = lc.sm_count * 16;
@@ -482,13 +514,13 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
             if (per_sm > 4) per_sm = 4;
             k_numeric_rank<false, 512><<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
                 job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_RANK * stride, h_counts[NUM_RANK],
-                ticket_stride, (int)cols, c_ptr, c_idx, c_val, d_work_counter);
+                ticket_stride, (int)cols, c_ptr, c_idx, c_val, d_work_counter, saved);
         } else {
             const int64_t window = cols < (1 << 20) ? cols : (1 << 20);
             const size_t smem = (size_t)(window / 8 + window / 32);
             k_numeric_rank<true, 1024><<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count), 1024, smem, lc.stream>>>(
                 job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_RANK * stride, h_counts[NUM_RANK],
-                ticket_stride, (int)window, c_ptr, c_idx, c_val, d_work_counter);
+                ticket_stride, (int)window, c_ptr, c_idx, c_val, d_work_counter, saved);
         }
         SB_LAUNCH_CHECK(lc);
     }
