@@ -103,7 +103,7 @@ struct StepB { int hs, he; double w; };          // hs == he: nothing to contrac
 template <bool UPPER>
 __global__ void __launch_bounds__(1024, 1)
 k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __restrict__ t_kc,
-                const double* __restrict__ t_val, TriplePlan plan, int row_begin, int nrows, int win_cap, int red_pct,
+                const double* __restrict__ t_val, TriplePlan plan, int row_begin, int nrows, int win_cap,
                 double* __restrict__ C, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ TripleScratch S;
@@ -144,10 +144,6 @@ k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __r
         const int h_begin = __ldg(H.ptr + i), h_end = __ldg(H.ptr + i + 1);
         // zeros left of the covered columns: below the diagonal (upper mode) / left of column k0
         if (first_panel) triple_stream_out(row, nullptr, UPPER ? lo : plan.k0);
-        // the segment [lo, p1c) is split: columns [lo, mid) accumulate in shared memory, columns [mid, p1c) directly in
-        // C with L2 reductions (zeroed here first; they stay L2 resident while the item runs)
-        const int mid = lo + min(win_cap, ((p1c - lo) * (100 - red_pct) + 99) / 100);
-        for (int t = mid + tid; t < p1c; t += nt) row[t] = 0.0;
         unsigned p2 = 0;
         for (int base = h_begin; base < h_end; base += nt) {
             const int cnt = min(nt, h_end - base);
@@ -257,8 +253,7 @@ k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __r
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             if (k[u] >= lo) {
-                                const double x = wv[u] * v[u];
-                                if (k[u] < mid) atomicAdd(acc + (k[u] - lo), x); else atomicAdd(row + k[u], x);
+                                atomicAdd(acc + (k[u] - lo), wv[u] * v[u]);
                                 ++p2;
                             }
                         }
@@ -270,7 +265,7 @@ k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __r
         }
         p2_total += p2;
         // segment out (coalesced 128-bit streaming stores) and cleared for the next item
-        const int count = mid - lo;                        // the shared part of the segment
+        const int count = p1c - lo;
         double* dst = row + lo;
         const int head = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1);
         if (head && tid == 0 && count > 0) { st_stream_f64(dst, acc[0]); acc[0] = 0.0; }
@@ -335,7 +330,7 @@ __device__ __forceinline__ double ld_keep_f64(const double* p, unsigned long lon
 template <bool UPPER>
 __global__ void __launch_bounds__(1024, 1)
 k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __restrict__ t_kc,
-              const double* __restrict__ t_val, TriplePlan plan, int row_begin, int nrows, int win_cap, int red_pct,
+              const double* __restrict__ t_val, TriplePlan plan, int row_begin, int nrows, int win_cap,
               double* __restrict__ C, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ TripleScratch S;
@@ -374,10 +369,6 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
         const int32_t* hp = t_ptr + (size_t)p * H.cols;
         const int h_begin = __ldg(H.ptr + i), h_end = __ldg(H.ptr + i + 1);
         if (first_panel) triple_stream_out(row, nullptr, UPPER ? lo : plan.k0);
-        // the segment [lo, p1c) is split: columns [lo, mid) accumulate in shared memory, columns [mid, p1c) directly in
-        // C with L2 reductions (zeroed here first; they stay L2 resident while the item runs)
-        const int mid = lo + min(win_cap, ((p1c - lo) * (100 - red_pct) + 99) / 100);
-        for (int t = mid + tid; t < p1c; t += nt) row[t] = 0.0;
         unsigned p2 = 0;
         for (int base = h_begin; base < h_end; base += nt) {
             const int cnt = min(nt, h_end - base);
@@ -449,8 +440,7 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
                             const bool more = x + 32 < ee;
                             const int2 kcn = more ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
                             const double vn = more ? ld_keep_f64(pv, keep) : 0.0;
-                            const double x = wt[kc.y] * v;
-                            if (kc.x < mid) atomicAdd(acc + (kc.x - lo), x); else atomicAdd(row + kc.x, x);
+                            atomicAdd(acc + (kc.x - lo), wt[kc.y] * v);
                             kc = kcn;
                             v = vn;
                         }
@@ -463,8 +453,7 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
                             const int2 kcn = more ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
                             const double vn = more ? ld_keep_f64(pv, keep) : 0.0;
                             if (kc.x >= lo) {
-                                const double x = wt[kc.y] * v;
-                                if (kc.x < mid) atomicAdd(acc + (kc.x - lo), x); else atomicAdd(row + kc.x, x);
+                                atomicAdd(acc + (kc.x - lo), wt[kc.y] * v);
                                 ++p2;
                             }
                             kc = kcn;
@@ -477,7 +466,7 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
             __syncthreads();                               // tables are rewritten by the next slice / item
         }
         p2_total += p2;
-        const int count = mid - lo;                        // the shared part of the segment
+        const int count = p1c - lo;
         double* dst = row + lo;
         const int head = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1);
         if (head && tid == 0 && count > 0) { st_stream_f64(dst, acc[0]); acc[0] = 0.0; }
@@ -559,16 +548,7 @@ cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q
     const int n = H.rows;
     if (nrows <= 0 || n <= 0) return cudaSuccess;
     const size_t fixed = sizeof(TripleScratch) + 1024;                    // static scratch + per-block reserve
-    // Share of every segment that accumulates with L2 reductions instead of shared-memory adds.  Both are bounded by an
-    // atomic unit -- shared-memory float64 compare-and-swap adds by the SM's (2 cycles per lane: ~150 G adds/s chip-wide,
-    // measured 146-161 G/s in these kernels), reductions by L2's (197 G/s, scripts/micro/atomic_bw.cu) -- and the two
-    // work side by side.
-    int red_pct = env_int("SPGEMM_B200_TRIPLE_RED_PCT", 55);
-    if (red_pct < 0) red_pct = 0;
-    if (red_pct > 95) red_pct = 95;
-    int win = ((plan.panel_w * (100 - red_pct) + 99) / 100 + 1) & ~1;
-    if (win < 2) win = 2;
-    if (win > plan.panel_w) win = (plan.panel_w + 1) & ~1;
+    const int win = plan.panel_w;
     // 1, 2 or 4 blocks per SM of 1024 / 512 / 256 threads (32 warps per SM at <= 64 registers)
     auto smem_of = [&](int threads) { return q_runs ? triple_runs_smem(win, threads) : triple_window_smem(win, threads); };
     int per_sm = 1;
@@ -589,14 +569,14 @@ cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q
     const size_t smem = smem_of(threads);
     if (q_runs) {
         if (upper_only)
-            k_triple_runs<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, red_pct, d_c, d_counters);
+            k_triple_runs<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
         else
-            k_triple_runs<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, red_pct, d_c, d_counters);
+            k_triple_runs<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
     } else {
         if (upper_only)
-            k_triple_panels<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, red_pct, d_c, d_counters);
+            k_triple_panels<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
         else
-            k_triple_panels<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, red_pct, d_c, d_counters);
+            k_triple_panels<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
     }
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
