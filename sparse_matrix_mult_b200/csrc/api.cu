@@ -516,36 +516,29 @@ static void zero_nt(double* p, size_t count) {
 // zero (symmetric dense mode, triple product): only the upper trapezoids cross PCIe, host threads zero the rest.
 // The n rows are cut into fixed row blocks of kUpperBlocks-th of the matrix; block g (rows [gG, (g+1)G)) sends
 // columns [gG, n) as one 2-D copy and has columns [0, gG) zeroed on the host.  Halves the bytes on the link.
-// The zero fill is work any thread can do whoever owns the rows: share `part` of `nparts` (the multi-GPU driver
-// passes its GPU's index so the lower triangle is split evenly over all workers; one GPU: 0 of 1) takes the blocks
-// g = part (mod nparts), on `SPGEMM_B200_ZERO_THREADS` threads (default: the host's cores / nparts, at most 8).
-// d_c holds rows [r0, r1) only; c_host is the full n-column host matrix.
+// The zero fill (class ZeroFill) is work any thread can do whoever owns the rows: share `part` of `nparts` (the
+// multi-GPU driver passes its GPU's index so the lower triangle is split evenly over all workers; one GPU: 0 of 1)
+// takes the blocks g = part (mod nparts), on `SPGEMM_B200_ZERO_THREADS` threads (default: the host's cores / nparts,
+// at most 8).  d_c holds rows [r0, r1) only; c_host is the full n-column host matrix.
 constexpr int kUpperBlocks = 256;
 
-cudaError_t d2h_upper_rows(const double* d_c, int n, int r0, int r1, double* c_host, int part, int nparts) {
-    Ctx& g = cx();
-    if (n <= 0) return cudaSuccess;
-    const int G = (n + kUpperBlocks - 1) / kUpperBlocks;          // rows per block
-    cudaError_t err = cudaSuccess;
-    for (int b0 = (r0 / G) * G; b0 < r1 && err == cudaSuccess; b0 += G) {
-        const int s0 = b0 > r0 ? b0 : r0, s1 = b0 + G < r1 ? b0 + G : r1;     // this call's rows of the block
-        if (s1 <= s0) continue;
-        err = cudaMemcpy2DAsync(c_host + (size_t)s0 * n + b0, (size_t)n * 8, d_c + (size_t)(s0 - r0) * n + b0,
-                                (size_t)n * 8, (size_t)(n - b0) * 8, (size_t)(s1 - s0), cudaMemcpyDeviceToHost, g.stream);
-        g.stats.bytes_d2h += (int64_t)(n - b0) * (s1 - s0) * 8;
-    }
-    // zero this share of the lower-left rectangles on the host meanwhile
-    // (measured, cfg 5: the copy alone takes 123 ms on one GPU -- PCIe at 52 GB/s; with 2 / 4 / 8 / 16 zeroing threads
-    //  beside it 143 / 142 / 138 / 138 ms on a 32-core host.  On 2 - 8 GPUs the copy + zero fill takes ~105 ms whatever
-    //  the thread count: 12.8 GB written into host memory at ~120 GB/s, the host's memory write bandwidth --
-    //  profiles/r2/multi_gpu.md)
+// The zero fill runs on its own host threads from the START of a call (it needs nothing from the GPU), so that it
+// overlaps the operand upload and the kernels and leaves the PCIe copy of the result alone with the memory bus:
+// cfg 5 end to end on one GPU 169 -> 155 ms.
+void ZeroFill::start(double* c_host, int n, int part, int nparts) {
+    if (n <= 0 || !c_host) return;
+    // (measured, cfg 5: the copy alone takes 123 ms on one GPU -- PCIe at 52 GB/s; started together with the copy,
+    //  2 / 4 / 8 / 16 zeroing threads make it 143 / 142 / 138 / 138 ms on a 32-core host.  On 2 - 8 GPUs copy + zero fill
+    //  take ~105 ms whatever the thread count: 12.8 GB written into host memory at ~120 GB/s, the host's memory write
+    //  bandwidth -- profiles/r2/multi_gpu.md)
     unsigned hw = std::thread::hardware_concurrency();
     int nthreads = hw == 0 ? 4 : (int)hw / (nparts > 0 ? nparts : 1);
     if (nthreads > 8) nthreads = 8;
     if (nthreads < 1) nthreads = 1;
     if (const char* ev = getenv("SPGEMM_B200_ZERO_THREADS")) nthreads = atoi(ev);      // 0 = skip (experiments only)
     if ((size_t)n * n < ((size_t)1 << 22) && nthreads > 1) nthreads = 1;
-    if (nthreads <= 0) return err;
+    if (nthreads <= 0) return;
+    const int G = (n + kUpperBlocks - 1) / kUpperBlocks;
     const int nblocks = (n + G - 1) / G;
     auto zero_blocks = [=](int t) {
         // blocks of this share, dealt to the threads from the bottom of the matrix up (widest rectangles first)
@@ -558,10 +551,25 @@ cudaError_t d2h_upper_rows(const double* d_c, int n, int r0, int r1, double* c_h
         }
         _mm_sfence();
     };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < nthreads; ++t) pool.emplace_back(zero_blocks, t);
-    zero_blocks(0);
-    for (auto& th : pool) th.join();
+    for (int t = 0; t < nthreads; ++t) threads_.emplace_back(zero_blocks, t);
+}
+void ZeroFill::join() {
+    for (auto& th : threads_) th.join();
+    threads_.clear();
+}
+
+cudaError_t d2h_upper_rows(const double* d_c, int n, int r0, int r1, double* c_host) {
+    Ctx& g = cx();
+    if (n <= 0) return cudaSuccess;
+    const int G = (n + kUpperBlocks - 1) / kUpperBlocks;          // rows per block
+    cudaError_t err = cudaSuccess;
+    for (int b0 = (r0 / G) * G; b0 < r1 && err == cudaSuccess; b0 += G) {
+        const int s0 = b0 > r0 ? b0 : r0, s1 = b0 + G < r1 ? b0 + G : r1;     // this call's rows of the block
+        if (s1 <= s0) continue;
+        err = cudaMemcpy2DAsync(c_host + (size_t)s0 * n + b0, (size_t)n * 8, d_c + (size_t)(s0 - r0) * n + b0,
+                                (size_t)n * 8, (size_t)(n - b0) * 8, (size_t)(s1 - s0), cudaMemcpyDeviceToHost, g.stream);
+        g.stats.bytes_d2h += (int64_t)(n - b0) * (s1 - s0) * 8;
+    }
     return err;
 }
 
@@ -1085,7 +1093,10 @@ int spgemm_b200_dense(int m, int k, int n, const int32_t* a_indptr, const int32_
     begin_call();
     spgemm_b200_mat *a = nullptr, *b = nullptr;
     double* d_c = nullptr;
+    ZeroFill zero;                                 // symmetric result: the host zeroes the lower triangle meanwhile
+    if (upper_only && !mirror && m == n) zero.start(c_host, n, 0, 1);
     auto done = [&](int code) {
+        zero.join();
         dfree(d_c); mat_release(a); mat_release(b);
         return code;
     };
@@ -1109,7 +1120,7 @@ int spgemm_b200_dense(int m, int k, int n, const int32_t* a_indptr, const int32_
     mark(EV_POST);
     if (elems) {
         NvtxRange nv("spgemm_b200:d2h");
-        if (upper_only && !mirror && m == n) e = d2h_upper_rows(d_c, n, 0, n, c_host, 0, 1);
+        if (upper_only && !mirror && m == n) e = d2h_upper_rows(d_c, n, 0, n, c_host);
         else { e = cudaMemcpyAsync(c_host, d_c, elems * 8, cudaMemcpyDeviceToHost, g.stream); g.stats.bytes_d2h += (int64_t)elems * 8; }
         if (e != cudaSuccess) return done(fail(SPGEMM_B200_ERR_CUDA, "dense result copy", e));
     }
@@ -1169,7 +1180,10 @@ int spgemm_b200_triple(int n, int k, const int32_t* h_indptr, const int32_t* h_i
     spgemm_b200_mat *h = nullptr, *q = nullptr;
     double* d_c = nullptr;
     unsigned long long* d_cnt = nullptr;
+    ZeroFill zero;                                 // upper mode: the host zeroes the lower triangle meanwhile
+    if (mode == SPGEMM_B200_TRIPLE_UPPER) zero.start(c_host, n, 0, 1);
     auto done = [&](int code) {
+        zero.join();
         dfree(d_c); dfree(d_cnt);
         mat_release(h); mat_release(q);
         return code;
@@ -1195,7 +1209,7 @@ int spgemm_b200_triple(int n, int k, const int32_t* h_indptr, const int32_t* h_i
     e = cudaMemcpyAsync(hc, d_cnt, 16, cudaMemcpyDeviceToHost, g.stream);
     if (e == cudaSuccess && elems) {
         NvtxRange nv("spgemm_b200:d2h");
-        if (mode == SPGEMM_B200_TRIPLE_UPPER) e = d2h_upper_rows(d_c, n, 0, n, c_host, 0, 1);
+        if (mode == SPGEMM_B200_TRIPLE_UPPER) e = d2h_upper_rows(d_c, n, 0, n, c_host);
         else { e = cudaMemcpyAsync(c_host, d_c, elems * 8, cudaMemcpyDeviceToHost, g.stream); g.stats.bytes_d2h += (int64_t)elems * 8; }
     }
     mark(EV_D2H);
@@ -1257,8 +1271,12 @@ int spgemm_b200_copy_upper_to_host(double* host_dst, const double* d_src, int n)
     if (n > 0 && (!host_dst || !d_src)) return fail(SPGEMM_B200_ERR_ARG, "copy_upper_to_host: null pointer");
     ENTER_DEFAULT();
     cx().stats.bytes_d2h = 0;
-    CU(d2h_upper_rows(d_src, n, 0, n, host_dst, 0, 1));
-    CU(cudaStreamSynchronize(cx().stream));
+    ZeroFill zero;
+    zero.start(host_dst, n, 0, 1);
+    cudaError_t e = d2h_upper_rows(d_src, n, 0, n, host_dst);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cx().stream);
+    zero.join();
+    if (e != cudaSuccess) return fail(SPGEMM_B200_ERR_CUDA, "copy_upper_to_host", e);
     return SPGEMM_B200_OK;
 }
 

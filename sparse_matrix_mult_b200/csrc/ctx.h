@@ -7,6 +7,8 @@
 
 #include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/spgemm_b200.h"
 #include "internal.h"
@@ -136,9 +138,18 @@ int row_costs_impl(const spgemm_b200_mat* a, const spgemm_b200_mat* b, const spg
                    int dense_cols, int64_t* d_costs);
 void partition_costs(const int64_t* costs, int rows, int parts, int32_t* bounds);
 // rows [r0, r1) of an n-column result whose entries left of the diagonal are zero: columns [block start, n) of
-// each fixed row block cross PCIe; this caller's share (part of nparts) of the lower triangle is zeroed by host
-// threads.  d_c holds the rows [r0, r1) only.
-cudaError_t d2h_upper_rows(const double* d_c, int n, int r0, int r1, double* c_host, int part, int nparts);
+// each fixed row block cross PCIe (asynchronous, on the context's stream).  d_c holds the rows [r0, r1) only.
+cudaError_t d2h_upper_rows(const double* d_c, int n, int r0, int r1, double* c_host);
+// host threads zeroing share `part` of `nparts` of the rectangles left of those blocks (the lower triangle of the
+// n x n host matrix); started at the beginning of a call, joined before it returns
+class ZeroFill {
+public:
+    void start(double* c_host, int n, int part, int nparts);
+    void join();
+    ~ZeroFill() { join(); }
+private:
+    std::vector<std::thread> threads_;
+};
 
 // pinned host cache (process-wide)
 void* host_cache_alloc(size_t bytes);

@@ -188,6 +188,13 @@ void worker(Job* job, int d) {
     CallGuard guard(c);
     Ctx& g = cx();
     begin_call();
+    // symmetric dense result: every worker zeroes its share of the lower triangle on host threads, from the start
+    ZeroFill zero;
+    {
+        const bool square = job->kind == K_TRIPLE || job->a.rows == job->b.cols;
+        if (job->kind != K_CSR && job->upper_only && square)
+            zero.start(job->c_host, job->kind == K_TRIPLE ? job->a.rows : job->b.cols, d, job->n_gpus);
+    }
     spgemm_b200_mat *a = nullptr, *b = nullptr, *ht = nullptr;
     double* d_c = nullptr;
     unsigned long long* d_cnt = nullptr;
@@ -272,8 +279,7 @@ void worker(Job* job, int d) {
                 NvtxRange nv("spgemm_b200:multi:d2h");
                 cudaError_t e = cudaSuccess;
                 if (job->upper_only && square) {
-                    // every worker zeroes its share of the lower triangle, whether or not it owns rows
-                    e = d2h_upper_rows(d_c, n, r0, r1, job->c_host, d, job->n_gpus);
+                    if (r1 > r0) e = d2h_upper_rows(d_c, n, r0, r1, job->c_host);
                 } else if (r1 > r0) {
                     e = cudaMemcpyAsync(job->c_host + (size_t)r0 * n, d_c, (size_t)(r1 - r0) * n * 8,
                                         cudaMemcpyDeviceToHost, g.stream);
@@ -290,6 +296,7 @@ void worker(Job* job, int d) {
         if (rc) job->set_error(rc);
     }
     cudaStreamSynchronize(g.stream);
+    zero.join();
     finish_stats();
     job->stats[d] = g.stats;
     dfree(d_c); dfree(d_cnt);
