@@ -519,21 +519,22 @@ static void zero_nt(double* p, size_t count) {
 // The zero fill (class ZeroFill) is work any thread can do whoever owns the rows: share `part` of `nparts` (the
 // multi-GPU driver passes its GPU's index so the lower triangle is split evenly over all workers; one GPU: 0 of 1)
 // takes the blocks g = part (mod nparts), on `SPGEMM_B200_ZERO_THREADS` threads (default: the host's cores / nparts,
-// at most 8).  d_c holds rows [r0, r1) only; c_host is the full n-column host matrix.
+// at most 4).  d_c holds rows [r0, r1) only; c_host is the full n-column host matrix.
 constexpr int kUpperBlocks = 256;
 
-// The zero fill runs on its own host threads from the START of a call (it needs nothing from the GPU), so that it
-// overlaps the operand upload and the kernels and leaves the PCIe copy of the result alone with the memory bus:
-// cfg 5 end to end on one GPU 169 -> 155 ms.
+// The zero fill runs on its own host threads from the START of a call (it needs nothing from the GPU), beside the
+// operand upload, the kernels and the copy of the result.  It does not make the call shorter by much: the 16-core
+// hosts of this pool sustain ~80-120 GB/s of memory traffic in total, which the zero fill (6.4 GB for cfg 5), the
+// upload (0.9 GB) and the DMA writes of the result (6.4 GB) share -- measured end to end on one GPU, cfg 5:
+// 170.6 / 167.4 / 177.0 ms with 2 / 4 / 8 zeroing threads (more threads slow the upload down: 16 -> 38 ms), against
+// 169-173 ms when the zero fill only started with the copy (profiles/r2/e2e_notes.md).
 void ZeroFill::start(double* c_host, int n, int part, int nparts) {
     if (n <= 0 || !c_host) return;
-    // (measured, cfg 5: the copy alone takes 123 ms on one GPU -- PCIe at 52 GB/s; started together with the copy,
-    //  2 / 4 / 8 / 16 zeroing threads make it 143 / 142 / 138 / 138 ms on a 32-core host.  On 2 - 8 GPUs copy + zero fill
-    //  take ~105 ms whatever the thread count: 12.8 GB written into host memory at ~120 GB/s, the host's memory write
-    //  bandwidth -- profiles/r2/multi_gpu.md)
+    // (the copy alone takes 123 ms on one GPU -- PCIe at 52 GB/s.  On 2 - 8 GPUs copy + zero fill take ~105 ms whatever
+    //  the thread count: 12.8 GB written into host memory at ~120 GB/s, the host's memory write bandwidth)
     unsigned hw = std::thread::hardware_concurrency();
     int nthreads = hw == 0 ? 4 : (int)hw / (nparts > 0 ? nparts : 1);
-    if (nthreads > 8) nthreads = 8;
+    if (nthreads > 4) nthreads = 4;
     if (nthreads < 1) nthreads = 1;
     if (const char* ev = getenv("SPGEMM_B200_ZERO_THREADS")) nthreads = atoi(ev);      // 0 = skip (experiments only)
     if ((size_t)n * n < ((size_t)1 << 22) && nthreads > 1) nthreads = 1;
