@@ -529,7 +529,7 @@ cudaError_t launch_add_const(const LaunchCtx& lc, int64_t* d_costs, int n, long 
 // the row takes part in (a; upper mode: the panels right of the diagonal), the entries of H^T in those panels --
 // the fraction (n - i) / n of all of them in upper mode -- are multiplied and accumulated (b), and every row of C is
 // written in full, zeros included (c).  (a, b, c) were fitted to the per-rank kernel times of cfg 5 on four B200s
-// (profiles/r2/multi_gpu.md): (0.005, 0.53, 0.25) ms per 10^8 units with the banded-Q kernel, i.e. the expansion is
+// (profiles/r2/SUMMARY.md): (0.005, 0.53, 0.25) ms per 10^8 units with the banded-Q kernel, i.e. the expansion is
 // almost free there; the general kernel pays ~100 instructions per 32 products.  SPGEMM_B200_TRIPLE_COST="a,b,c"
 // overrides them.  One warp per row.
 __global__ void __launch_bounds__(256)

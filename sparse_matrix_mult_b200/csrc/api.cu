@@ -527,7 +527,7 @@ constexpr int kUpperBlocks = 256;
 // hosts of this pool sustain ~80-120 GB/s of memory traffic in total, which the zero fill (6.4 GB for cfg 5), the
 // upload (0.9 GB) and the DMA writes of the result (6.4 GB) share -- measured end to end on one GPU, cfg 5:
 // 170.6 / 167.4 / 177.0 ms with 2 / 4 / 8 zeroing threads (more threads slow the upload down: 16 -> 38 ms), against
-// 169-173 ms when the zero fill only started with the copy (profiles/r2/e2e_notes.md).
+// 169-173 ms when the zero fill only started with the copy (profiles/r2/e2e_probe_early_zero_fill.jsonl).
 void ZeroFill::start(double* c_host, int n, int part, int nparts) {
     if (n <= 0 || !c_host) return;
     // (the copy alone takes 123 ms on one GPU -- PCIe at 52 GB/s.  On 2 - 8 GPUs copy + zero fill take ~105 ms whatever

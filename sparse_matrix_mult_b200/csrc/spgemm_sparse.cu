@@ -232,7 +232,7 @@ k_numeric_warp(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __res
 // (Two variants measured slower and were removed -- DESIGN.md section 7: accumulating by rank in shared memory, in
 //  rank windows (round 1), and a block-wide shared-memory hash table of (column, value) scattered by bitmap rank,
 //  one traversal of the products instead of two (round 2: cfg 4r numeric 6.7 ms against 3.6 ms, barrier stalls and
-//  compare-and-swap contention on the hub columns of power-law inputs; profiles/r2/numeric_hash_bins.md).)
+//  compare-and-swap contention on the hub columns of power-law inputs; profiles/r2/SUMMARY.md).)
 template <bool COMPACT>
 struct RankTable {
     unsigned* bits;      // COMPACT: bits[words];            else: interleaved {bits, prefix}
