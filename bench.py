@@ -128,6 +128,18 @@ def describe(w, name, recount=False):
     return info, flops
 
 
+def config_of(info, w, n_gpus):
+    """`config` of a bench line -- identical on both arms: the workload and how the GPU arm treats it (whether L2 is
+    flushed between timed steps, what a step contains, how many GPUs share it)."""
+    kind = w["kind"]
+    out = dict(info)
+    out["gpu_l2"] = L2_NOTE[operands_small(w["a"], w["b"])]
+    out["gpu_step"] = ("H^T is rebuilt on the device inside every timed step" if kind == "triple" else
+                       "analysis + symbolic + numeric phases" if kind == "sparse" else "one kernel")
+    out["n_gpus"] = int(n_gpus)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
@@ -272,7 +284,8 @@ def run_reference_arm(args, w, name, info, threads):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(info, sample=desc, omp_threads=threads),
+            "config": config_of(info, w, args.gpus),
+            "run": {"sample": desc, "omp_threads": threads, "step": "one call of the reference C routine on the sample"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -615,9 +628,8 @@ def run_ours(args, w, name, info, flops, rank, world, threads):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(info, parallelism=f"rows sharded over {world} GPU(s), flop-balanced", l2=L2_NOTE[small],
-                           step="H^T is rebuilt on the device inside every timed step" if kind == "triple" else
-                                "analysis + symbolic + numeric phases" if kind == "sparse" else "one kernel"),
+            "config": config_of(info, w, world),
+            "run": {"sample": "full workload", "parallelism": f"rows sharded over {world} GPU(s), cost-balanced"},
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline_of(kind, name, t, peak, peak_src),
             "phases_ms": {k: round(t["stats"].get(k, 0.0), 4) for k in
