@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(THREADS)
 k_numeric_rank(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __restrict__ b_sorted_flag,
                const int32_t* __restrict__ list, int count, int stride, int window,
                const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, double* __restrict__ c_val,
-               int32_t* __restrict__ work_counter, SavedBitmaps saved, int sub_entries) {
+               int32_t* __restrict__ work_counter, SavedBitmaps saved) {
     extern __shared__ unsigned s_dynu[];
     RankTable<COMPACT> tab;
     tab.bits = s_dynu;
@@ -345,42 +345,11 @@ k_numeric_rank(Csr A, Csr B, int row_begin, int upper_only, const int32_t* __res
                 }
             }
             double* gv = c_val + out;
-            if (sub_entries <= 0 || !b_sorted || nnz_w <= 2 * sub_entries) {
-                for (int t = threadIdx.x; t < nnz_w; t += THREADS) gv[t] = 0.0;
-                __syncthreads();
-                // pass 2: values
-                expand_row_block<true>(A, B, a_begin, a_end, wl, wh, col_windowed, b_sorted, s_seg,
-                                       [&](int c, double v) { atomicAdd(gv + tab.rank(c - w0), v); });
-            } else {
-                // Heavy row: its slice of C.val (up to several MB) does not stay in L2 next to the slices of the other
-                // blocks, and a reduction that misses L2 is a DRAM read-modify-write.  Pass 2 therefore goes through the
-                // row in COLUMN sub-windows of ~sub_entries output entries each (cut at table-unit boundaries found in
-                // the rank prefix): the sub-window's values are zeroed, then only the products inside it are formed
-                // (rows of B are sorted: the bounds are binary-searched inside each row of B) and reduced into a few
-                // hundred KB that stay L2 resident.
-                const int unit_cols = COMPACT ? 128 : 32;
-                int u_lo = 0;                                          // first table unit of the sub-window
-                while (u_lo < units) {
-                    const int r_lo = COMPACT ? (int)tab.pre[u_lo] : (int)tab.bits[2 * u_lo + 1];
-                    // largest u_hi with prefix(u_hi) <= r_lo + sub_entries (at least one unit)
-                    int a = u_lo + 1, b = units;
-                    while (a < b) {
-                        const int mid = (a + b + 1) >> 1;
-                        const int pm = mid >= units ? nnz_w : COMPACT ? (int)tab.pre[mid] : (int)tab.bits[2 * mid + 1];
-                        if (pm <= r_lo + sub_entries) a = mid; else b = mid - 1;
-                    }
-                    const int u_hi = a;                                // exclusive end unit (may equal units)
-                    const int r_hi = u_hi < units ? (COMPACT ? (int)tab.pre[u_hi] : (int)tab.bits[2 * u_hi + 1]) : nnz_w;
-                    for (int t = r_lo + threadIdx.x; t < r_hi; t += THREADS) gv[t] = 0.0;
-                    __syncthreads();
-                    const int c_lo = max(wl, w0 + u_lo * unit_cols), c_hi = min(wh, w0 + u_hi * unit_cols);
-                    if (r_hi > r_lo && c_hi > c_lo)
-                        expand_row_block<true>(A, B, a_begin, a_end, c_lo, c_hi, true, b_sorted, s_seg,
-                                               [&](int c, double v) { atomicAdd(gv + tab.rank(c - w0), v); });
-                    __syncthreads();
-                    u_lo = u_hi;
-                }
-            }
+            for (int t = threadIdx.x; t < nnz_w; t += THREADS) gv[t] = 0.0;
+            __syncthreads();
+            // pass 2: values
+            expand_row_block<true>(A, B, a_begin, a_end, wl, wh, col_windowed, b_sorted, s_seg,
+                                   [&](int c, double v) { atomicAdd(gv + tab.rank(c - w0), v); });
             out += nnz_w;
             __syncthreads();
         }
@@ -535,9 +504,6 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
             if (h_counts[NUM_RANK] % cand != 0) { ticket_stride = cand % h_counts[NUM_RANK]; break; }
         }
         if (ticket_stride == 0) ticket_stride = 1;
-        // heavy rows take pass 2 in column sub-windows of this many output entries (0 = off)
-        int sub_entries = 32768;
-        if (const char* v = getenv("SPGEMM_B200_RANK_SUBWIN")) sub_entries = atoi(v);
         // pair layout (8 B per 32 columns) while at least two blocks fit an SM; else the compact layout (5 B per
         // 32 columns) with one 1024-thread block per SM and a window of up to 2^20 columns
         const int64_t cols = ((int64_t)job.B.cols + 127) & ~(int64_t)127;
@@ -548,13 +514,13 @@ cudaError_t launch_numeric(const LaunchCtx& lc, const SparseJob& job, const int3
             if (per_sm > 4) per_sm = 4;
             k_numeric_rank<false, 512><<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count * per_sm), 512, smem, lc.stream>>>(
                 job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_RANK * stride, h_counts[NUM_RANK],
-                ticket_stride, (int)cols, c_ptr, c_idx, c_val, d_work_counter, saved, sub_entries);
+                ticket_stride, (int)cols, c_ptr, c_idx, c_val, d_work_counter, saved);
         } else {
             const int64_t window = cols < (1 << 20) ? cols : (1 << 20);
             const size_t smem = (size_t)(window / 8 + window / 32);
             k_numeric_rank<true, 1024><<<grid_for(h_counts[NUM_RANK], 1, lc.sm_count), 1024, smem, lc.stream>>>(
                 job.A, job.B, job.row_begin, up, job.d_b_sorted, d_lists + NUM_RANK * stride, h_counts[NUM_RANK],
-                ticket_stride, (int)window, c_ptr, c_idx, c_val, d_work_counter, saved, sub_entries);
+                ticket_stride, (int)window, c_ptr, c_idx, c_val, d_work_counter, saved);
         }
         SB_LAUNCH_CHECK(lc);
     }
