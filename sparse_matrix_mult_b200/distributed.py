@@ -61,26 +61,37 @@ def host_row_costs(a, b, kind, upper_only):
 
 
 # ------------------------------------------------------------------------------------------------------
-# broadcast of a CSR matrix from rank 0
-def _bcast_array(x, dtype, n, device, src=0):
-    t = torch.empty(n, dtype=dtype, device=device)
-    if dist.get_rank() == src:
-        t.copy_(torch.from_numpy(np.ascontiguousarray(x)).to(dtype))
-    dist.broadcast(t, src=src)
-    return t
+# broadcast of a CSR matrix from rank 0: one 24-byte header + ONE packed byte buffer per matrix
+def _packed_layout(rows, nnz):
+    """Byte offsets of indptr | indices | data inside the packed buffer (data 8-byte aligned) and its size."""
+    o_ptr = 0
+    o_idx = o_ptr + 4 * (rows + 1)
+    o_val = (o_idx + 4 * nnz + 7) & ~7
+    return o_ptr, o_idx, o_val, o_val + 8 * nnz
 
 
 def broadcast_csr(x, device):
-    """rank 0 passes a scipy CSR, the others None; returns (shape, indptr, indices, data) tensors on `device`."""
-    meta = torch.zeros(3, dtype=torch.int64, device=device)
+    """rank 0 passes a scipy CSR, the others None; returns (shape, indptr, indices, data) tensors on `device`.
+    Two collectives per matrix: the header (rows, cols, nnz) and the three arrays packed into one byte buffer
+    (round 1 sent a header and three arrays and synchronised the host in between)."""
+    meta = torch.zeros(3, dtype=torch.int64)
     if dist.get_rank() == 0:
         meta[:] = torch.tensor([x.shape[0], x.shape[1], x.nnz], dtype=torch.int64)
+    meta = meta.to(device)
     dist.broadcast(meta, src=0)
     rows, cols, nnz = (int(v) for v in meta.tolist())
-    src = x if dist.get_rank() == 0 else None
-    indptr = _bcast_array(src.indptr if src is not None else None, torch.int32, rows + 1, device)
-    indices = _bcast_array(src.indices if src is not None else None, torch.int32, nnz, device)
-    data = _bcast_array(src.data if src is not None else None, torch.float64, nnz, device)
+    o_ptr, o_idx, o_val, size = _packed_layout(rows, nnz)
+    buf = torch.empty(max(size, 8), dtype=torch.uint8, device=device)
+    if dist.get_rank() == 0:
+        host = np.zeros(max(size, 8), dtype=np.uint8)
+        host[o_ptr:o_idx].view(np.int32)[:] = np.ascontiguousarray(x.indptr, dtype=np.int32)
+        host[o_idx:o_idx + 4 * nnz].view(np.int32)[:] = np.ascontiguousarray(x.indices, dtype=np.int32)
+        host[o_val:o_val + 8 * nnz].view(np.float64)[:] = np.ascontiguousarray(x.data, dtype=np.float64)
+        buf.copy_(torch.from_numpy(host))
+    dist.broadcast(buf, src=0)
+    indptr = buf[o_ptr:o_idx].view(torch.int32)
+    indices = buf[o_idx:o_idx + 4 * nnz].view(torch.int32)
+    data = buf[o_val:o_val + 8 * nnz].view(torch.float64)
     return (rows, cols), indptr, indices, data
 
 
@@ -310,7 +321,7 @@ def bench_e2e(args, w, flops, rank, world, csr_bytes):
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        if kind == "dense" and os.environ.get("SPGEMM_B200_GATHER", "peer") == "peer":
+        if kind in ("dense", "triple") and os.environ.get("SPGEMM_B200_GATHER", "peer") == "peer":
             out = multiply_sharded_peer(a, b, kind, upper, device)          # gather fused into the kernels
             gather = "peer stores over NVLink from inside the compute kernels (CUDA IPC)"
             if rank == 0:
