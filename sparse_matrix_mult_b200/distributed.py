@@ -82,12 +82,11 @@ def broadcast_csr(x, device):
     rows, cols, nnz = (int(v) for v in meta.tolist())
     o_ptr, o_idx, o_val, size = _packed_layout(rows, nnz)
     buf = torch.empty(max(size, 8), dtype=torch.uint8, device=device)
-    if dist.get_rank() == 0:
-        host = np.zeros(max(size, 8), dtype=np.uint8)
-        host[o_ptr:o_idx].view(np.int32)[:] = np.ascontiguousarray(x.indptr, dtype=np.int32)
-        host[o_idx:o_idx + 4 * nnz].view(np.int32)[:] = np.ascontiguousarray(x.indices, dtype=np.int32)
-        host[o_val:o_val + 8 * nnz].view(np.float64)[:] = np.ascontiguousarray(x.data, dtype=np.float64)
-        buf.copy_(torch.from_numpy(host))
+    if dist.get_rank() == 0:                     # three copies straight into their slices of the packed buffer
+        buf[o_ptr:o_idx].view(torch.int32).copy_(torch.from_numpy(np.ascontiguousarray(x.indptr, dtype=np.int32)))
+        if nnz:
+            buf[o_idx:o_idx + 4 * nnz].view(torch.int32).copy_(torch.from_numpy(np.ascontiguousarray(x.indices, dtype=np.int32)))
+            buf[o_val:o_val + 8 * nnz].view(torch.float64).copy_(torch.from_numpy(np.ascontiguousarray(x.data, dtype=np.float64)))
     dist.broadcast(buf, src=0)
     indptr = buf[o_ptr:o_idx].view(torch.int32)
     indices = buf[o_idx:o_idx + 4 * nnz].view(torch.int32)
