@@ -182,6 +182,12 @@ SPGEMM_B200_API int spgemm_b200_mat_transpose(const spgemm_b200_mat *x, spgemm_b
 SPGEMM_B200_API int spgemm_b200_mat_sort(spgemm_b200_mat *x);
 SPGEMM_B200_API int spgemm_b200_mat_is_sorted(const spgemm_b200_mat *x);
 
+/* Keep (enable != 0) or drop the paneled transpose that spgemm_b200_triple_dev builds from this matrix when it is the
+   H of a triple product: a caller that multiplies with the same resident H repeatedly -- the iterations of an
+   inversion -- then pays for the transpose once.  The reference has no counterpart: it rebuilds
+   nothing because it never transposes (it dots t with every row of H, src/sparse_sparse_dense.cpp:201-216). */
+SPGEMM_B200_API int spgemm_b200_mat_cache_transpose(spgemm_b200_mat *x, int enable);
+
 SPGEMM_B200_API void spgemm_b200_mat_free(spgemm_b200_mat *m);
 
 /* Rows [row_begin, row_end) of C = A*B as a device-resident CSR result (row_end < 0 means all rows).

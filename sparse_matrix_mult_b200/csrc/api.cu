@@ -335,7 +335,7 @@ void host_cache_clear() {
 int alloc_mat(int rows, int cols, int64_t nnz, spgemm_b200_mat** out) {
     Ctx& g = cx();
     spgemm_b200_mat* m = new spgemm_b200_mat{rows, cols, nnz, nullptr, nullptr, nullptr, true, g.device,
-                                             nullptr, false, false, false, false, false, nullptr};
+                                             nullptr, false, false, false, false, false, nullptr, false, nullptr};
     int rc;
     if ((rc = dalloc(&m->ptr, (size_t)rows + 1)) || (rc = dalloc(&m->idx, (size_t)nnz)) ||
         (rc = dalloc(&m->val, (size_t)nnz))) {
@@ -369,8 +369,11 @@ int upload(int rows, int cols, const int32_t* ptr, const int32_t* idx, const dou
     return SPGEMM_B200_OK;
 }
 
+static void panel_cache_drop(spgemm_b200_mat* m);
+
 void mat_release(spgemm_b200_mat* m) {
     if (!m) return;
+    panel_cache_drop(m);
     if (m->owns) { dfree(m->ptr); dfree(m->idx); dfree(m->val); }
     dfree(m->d_flags);
     if (m->shadow) mat_release(m->shadow);
@@ -389,7 +392,7 @@ int transpose_impl(const spgemm_b200_mat* x, spgemm_b200_mat** out, bool sort_de
     Ctx& g = cx();
     NvtxRange nv("spgemm_b200:transpose");
     spgemm_b200_mat* t = new spgemm_b200_mat{x->cols, x->rows, x->nnz, nullptr, nullptr, nullptr, true, g.device,
-                                             nullptr, false, false, false, false, false, nullptr};
+                                             nullptr, false, false, false, false, false, nullptr, false, nullptr};
     int32_t *counts = nullptr, *cursor = nullptr;
     int64_t* tmp = nullptr;
     int rc;
@@ -464,7 +467,7 @@ int sorted_view(spgemm_b200_mat* m, spgemm_b200_mat** out) {
     if (!m->owns) {                                           // borrowed arrays are never modified: sort a copy
         if (m->shadow) { *out = m->shadow; return SPGEMM_B200_OK; }
         t = new spgemm_b200_mat{m->rows, m->cols, m->nnz, nullptr, nullptr, nullptr, true, g.device,
-                                nullptr, false, false, false, false, false, nullptr};
+                                nullptr, false, false, false, false, false, nullptr, false, nullptr};
         int rc;
         if ((rc = dalloc(&t->ptr, (size_t)m->rows + 1)) || (rc = dalloc(&t->idx, (size_t)m->nnz)) ||
             (rc = dalloc(&t->val, (size_t)m->nnz)) || (rc = dalloc(&t->d_flags, 8))) {
@@ -724,6 +727,20 @@ static void panels_release(PanelT& t) {
     dfree(t.ptr); dfree(t.kc); dfree(t.val);
     t = PanelT();
 }
+// A paneled transpose kept on its matrix (spgemm_b200_mat_cache_transpose): a caller that multiplies with the same H
+// again and again (the iterations of an inversion) pays for it once.
+struct PanelCache {
+    PanelT t;
+    TriplePlan plan;
+};
+static void panel_cache_drop(spgemm_b200_mat* m) {
+    if (!m->panel_cache) return;
+    PanelCache* c = static_cast<PanelCache*>(m->panel_cache);
+    panels_release(c->t);
+    delete c;
+    m->panel_cache = nullptr;
+}
+
 static int transpose_panels(const spgemm_b200_mat* h, const TriplePlan& plan, PanelT* out) {
     Ctx& g = cx();
     NvtxRange nv("spgemm_b200:transpose_panels");
@@ -765,13 +782,24 @@ int triple_rows(const spgemm_b200_mat* h, const spgemm_b200_mat* q, const spgemm
     {
         TriplePlan plan = triple_plan(h->rows, r0, upper_only != 0, h->nnz, h->cols);
         PanelT t;
-        if ((rc = transpose_panels(h, plan, &t))) return rc;
+        spgemm_b200_mat* hm = const_cast<spgemm_b200_mat*>(h);       // the kept transpose is a cache on the handle
+        PanelCache* kept = static_cast<PanelCache*>(hm->panel_cache);
+        if (kept && (kept->plan.k0 != plan.k0 || kept->plan.np != plan.np || kept->plan.panel_w != plan.panel_w)) {
+            panel_cache_drop(hm);
+            kept = nullptr;
+        }
+        if (kept) t = kept->t;
+        else if ((rc = transpose_panels(h, plan, &t))) return rc;
+        if (!kept && hm->cache_panels) {
+            kept = new PanelCache{t, plan};
+            hm->panel_cache = kept;
+        }
         mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
         NvtxRange nv("spgemm_b200:triple");
         const bool q_runs = q->checked && q->runs && env_mode("SPGEMM_B200_TRIPLE_GENERIC") == 0;
         e = launch_triple_panels(lctx(), view(h), view(q), q_runs, t.ptr, t.kc, t.val, plan, upper_only != 0, r0, r1 - r0,
                                  d_c, d_cnt);
-        panels_release(t);
+        if (!kept) panels_release(t);
     }
     if (e != cudaSuccess) return fail(SPGEMM_B200_ERR_CUDA, "triple kernel", e);
     g.stats.nnz_c = (int64_t)(r1 - r0) * h->rows;
@@ -926,7 +954,7 @@ int spgemm_b200_mat_wrap(int rows, int cols, int64_t nnz, const int32_t* d_indpt
     if (!out || !d_indptr || rows < 0 || cols < 0 || nnz < 0) return fail(SPGEMM_B200_ERR_ARG, "mat_wrap: bad argument");
     ENTER_DEFAULT();
     *out = new spgemm_b200_mat{rows, cols, nnz, const_cast<int32_t*>(d_indptr), const_cast<int32_t*>(d_indices),
-                               const_cast<double*>(d_values), false, cx().device, nullptr, false, false, false, false, false, nullptr};
+                               const_cast<double*>(d_values), false, cx().device, nullptr, false, false, false, false, false, nullptr, false, nullptr};
     return SPGEMM_B200_OK;
 }
 
@@ -936,6 +964,14 @@ int spgemm_b200_mat_transpose(const spgemm_b200_mat* x, spgemm_b200_mat** out) {
     int rc = ensure_checked(const_cast<spgemm_b200_mat*>(x));
     if (rc) return rc;
     return transpose_impl(x, out, true);
+}
+
+int spgemm_b200_mat_cache_transpose(spgemm_b200_mat* x, int enable) {
+    if (!x) return fail(SPGEMM_B200_ERR_ARG, "mat_cache_transpose: null argument");
+    ENTER_DEVICE(x->device);
+    x->cache_panels = enable != 0;
+    if (!enable) panel_cache_drop(x);
+    return SPGEMM_B200_OK;
 }
 
 int spgemm_b200_mat_sort(spgemm_b200_mat* x) {

@@ -29,6 +29,8 @@ struct spgemm_b200_mat {
     bool runs;                 // every row is one run of consecutive ascending columns (banded matrix)
     bool desc_sorted;          // rows sorted by DESCENDING column (set by the transpose)
     spgemm_b200_mat* shadow;   // row-sorted copy of a borrowed (owns == false) unsorted matrix, built on demand
+    bool cache_panels;         // keep the paneled transpose the triple product builds from this matrix (as H)
+    void* panel_cache;         // the kept transpose (api.cu: PanelCache), or null
 };
 struct spgemm_b200_result {
     int rows, cols;

@@ -88,6 +88,11 @@ class DeviceMatrix:
         _check(matrix_ops.get_lib().spgemm_b200_mat_transpose(self._h, ctypes.byref(h)), "spgemm_b200_mat_transpose")
         return DeviceMatrix(h, self.shape[::-1], self.nnz)
 
+    def cache_transpose(self, enable=True):
+        """Keep the paneled transpose triple_product() builds from this matrix (as H) across calls."""
+        _check(matrix_ops.get_lib().spgemm_b200_mat_cache_transpose(self._h, int(bool(enable))),
+               "spgemm_b200_mat_cache_transpose")
+
     def is_sorted(self):
         r = matrix_ops.get_lib().spgemm_b200_mat_is_sorted(self._h)
         if r < 0:

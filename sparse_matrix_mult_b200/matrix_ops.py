@@ -129,6 +129,7 @@ class MatrixOpsLibrary:
         L.spgemm_b200_set_stream.argtypes = [_vp]
         L.spgemm_b200_timer_stop.argtypes = [ctypes.POINTER(ctypes.c_double)]
         L.spgemm_b200_trim.argtypes = [ctypes.c_size_t]
+        L.spgemm_b200_mat_cache_transpose.argtypes = [_vp, ctypes.c_int]
         L.spgemm_b200_mat_sort.argtypes = [_vp]
         L.spgemm_b200_mat_is_sorted.argtypes = [_vp]
         L.spgemm_b200_multi_dense.argtypes = [ctypes.c_int] * 4 + csr + csr + [ctypes.c_int, _f64p]

@@ -349,3 +349,21 @@ def test_multi_gpu_without_peer_copies(monkeypatch):
     want = port.sparse_matrix_multiply(w["a"], w["b"], **w["kwargs"])
     for n_gpus in _gpu_counts():
         assert_dense_equal(sparse_matrix_multiply(w["a"], w["b"], n_gpus=n_gpus, **w["kwargs"]), want, f"no-peer n_gpus={n_gpus}")
+
+
+def test_triple_cached_transpose():
+    """DeviceMatrix.cache_transpose: the paneled transpose is kept on the H handle and reused by later calls with the
+    same panel plan, rebuilt when the plan changes (another first row), dropped on request."""
+    w = synthetic.workload("cfg3s")
+    h, q = w["a"], w["b"]
+    H, Q = dev.DeviceMatrix.from_scipy(h), dev.DeviceMatrix.from_scipy(q)
+    want = port.triple_product(h, q, 0)
+    H.cache_transpose(True)
+    for r0, r1 in [(0, 400), (0, 400), (100, 300), (100, 300), (0, 400)]:
+        out = dev.triple_product(H, Q, None, True, r0, r1)
+        np.testing.assert_allclose(out.to_host(), want[r0:r1], rtol=1e-12, atol=1e-14)
+        out.free()
+    H.cache_transpose(False)
+    out = dev.triple_product(H, Q, None, True, 0, 400)
+    np.testing.assert_allclose(out.to_host(), want, rtol=1e-12, atol=1e-14)
+    out.free()
