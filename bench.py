@@ -211,7 +211,7 @@ def traffic_for(name):
 
 
 DOMINANT = {"dense": "k_dense_rows_red", "sparse": "numeric phase (k_numeric_rank + k_numeric_warp<*>)",
-            "triple": "k_triple_window"}
+            "triple": "k_triple_runs"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -325,7 +325,8 @@ class Resident:
             costs, _ = dev.row_costs(self.A, ht if ht is not None else self.B, self.B if ht is not None else None,
                                      upper_only=(self.kind == "triple" or self.sym),
                                      dense_cols=(self.ncols if self.kind == "dense" else 0))
-            self.bounds = [int(x) for x in dev.partition_rows(costs, self.n_rows, world)]
+            self.bounds = [int(x) for x in dev.partition_rows(costs, self.n_rows, world,
+                                                             tail_indptr=a.indptr if self.kind == "triple" else None)]
             self.lib.spgemm_b200_device_free(costs)
             if ht is not None:
                 ht.free()

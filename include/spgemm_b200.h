@@ -227,6 +227,14 @@ SPGEMM_B200_API int spgemm_b200_row_costs(const spgemm_b200_mat *a, const spgemm
    chosen so every part carries ~total/parts of d_costs.  Replaces limits() for multi-GPU sharding. */
 SPGEMM_B200_API int spgemm_b200_partition(const int64_t *d_costs, int rows, int parts, int32_t *bounds_host);
 
+/* The same for the triple product, where the block that starts at row r also pays for the paneled transpose of rows
+   r.. of H: its cost is tail_coeff * (entries of H from row r on) + the sum of its rows' costs, and the partition
+   minimises the largest block cost.  indptr_host: H's row pointers on the host; tail_coeff in the units of
+   spgemm_b200_row_costs (SPGEMM_B200_TRIPLE_TAIL_COEFF below is the fitted value). */
+#define SPGEMM_B200_TRIPLE_TAIL_COEFF 8.6
+SPGEMM_B200_API int spgemm_b200_partition_tail(const int64_t *d_costs, const int32_t *indptr_host, double tail_coeff,
+                               int rows, int parts, int32_t *bounds_host);
+
 /* Raw device buffers from the library's stream-ordered pool (for callers without their own allocator),
    and plain copies on the library stream (synchronous on return). */
 SPGEMM_B200_API void *spgemm_b200_device_alloc(size_t bytes);

@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 NS=${1:-"2 4"}
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-timeout 1200 python -m pytest tests/test_gpu_device_api.py tests/test_multigpu.py -m gpu -q -x -k "multi or sharded" 2>&1 | tail -5
+timeout 1200 python -m pytest tests/test_gpu_device_api.py tests/test_multigpu.py -m gpu -q -x -k "multi or sharded or partition" 2>&1 | tail -5
 for N in $NS; do
   for W in cfg5; do
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + N)) \

@@ -535,10 +535,12 @@ cudaError_t launch_add_const(const LaunchCtx& lc, int64_t* d_costs, int n, long 
 // cost_i = a * P1_i * panels(i) + b * P2_i * (n - i) / n + c * n: the expansion is redone for every column panel
 // the row takes part in (a; upper mode: the panels right of the diagonal), the entries of H^T in those panels --
 // the fraction (n - i) / n of all of them in upper mode -- are multiplied and accumulated (b), and every row of C is
-// written in full, zeros included (c).  (a, b, c) were fitted to the per-rank kernel times of cfg 5 on four B200s
-// (profiles/r2/SUMMARY.md): (0.005, 0.53, 0.25) ms per 10^8 units with the banded-Q kernel, i.e. the expansion is
-// almost free there; the general kernel pays ~100 instructions per 32 products.  SPGEMM_B200_TRIPLE_COST="a,b,c"
-// overrides them.  One warp per row.
+// written in full, zeros included (c).  (b, c) were fitted jointly to the 15 per-rank step times of cfg 5 on 1, 2, 4
+// and 8 B200s (profiles/r2/SUMMARY.md): 0.454 and 0.289 ms per 10^8 units with the banded-Q kernel, i.e. c / b = 0.64,
+// together with the transposition term the partition adds per block (kTripleTailCoeff, ctx.h); the fit leaves +-3 %,
+// the spread between the GPUs of one box.  a is not identifiable on that matrix (P1_i is almost the same for every
+// row, so it is collinear with c) and stays small; the general kernel pays ~100 instructions per 32 products (a = 2, a
+// guess).  SPGEMM_B200_TRIPLE_COST="a,b,c" overrides them.  One warp per row.
 __global__ void __launch_bounds__(256)
 k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, int np, int panel_w, double ca, double cb, double cc,
                int64_t* __restrict__ costs) {
@@ -562,7 +564,7 @@ k_triple_costs(Csr H, Csr Q, Csr Ht, int upper_only, int np, int panel_w, double
 cudaError_t launch_triple_costs(const LaunchCtx& lc, const Csr& H, const Csr& Q, const Csr& Ht, bool upper_only,
                                 bool q_runs, int np, int panel_w, int64_t* d_costs) {
     if (H.rows <= 0) return cudaSuccess;
-    double ca = q_runs ? 0.05 : 2.0, cb = 1.0, cc = 0.5;
+    double ca = q_runs ? 0.05 : 2.0, cb = 1.0, cc = 0.64;
     if (const char* v = getenv("SPGEMM_B200_TRIPLE_COST")) sscanf(v, "%lf,%lf,%lf", &ca, &cb, &cc);
     k_triple_costs<<<(H.rows + 7) / 8, 256, 0, lc.stream>>>(H, Q, Ht, upper_only ? 1 : 0, np, panel_w > 0 ? panel_w : 1,
                                                            ca, cb, cc, d_costs);

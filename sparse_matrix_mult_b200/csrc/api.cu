@@ -851,6 +851,42 @@ void partition_costs(const int64_t* c, int rows, int parts, int32_t* bounds) {
     bounds[parts] = rows;
 }
 
+// Bottleneck partition with a start-dependent fixed cost: block p = rows [b_p, b_{p+1}) costs
+// tail_coeff * tail[b_p] + sum of its rows' costs, where tail[i] = units of rows i.. (a suffix sum; for the triple product
+// the entries of H from row i on, which the rank that starts at row i has to transpose).  Minimises the largest block
+// cost: binary search on the bound, greedy feasibility (taking as many rows as fit is optimal because the fixed cost
+// does not grow with the start row).
+void partition_costs_tail(const int64_t* c, const int64_t* tail, double tail_coeff, int rows, int parts, int32_t* bounds) {
+    std::vector<long double> cum((size_t)rows + 1, 0);
+    for (int i = 0; i < rows; ++i) cum[i + 1] = cum[i] + (long double)c[i] + 1;
+    auto fixed = [&](int r0) { return r0 < rows ? (long double)tail_coeff * (long double)tail[r0] : 0.0L; };
+    auto greedy = [&](long double limit, int32_t* out) {
+        int r0 = 0;
+        for (int p = 0; p < parts; ++p) {
+            if (out) out[p] = r0;
+            if (r0 >= rows) continue;
+            const long double room = limit - fixed(r0);
+            if (room <= 0) return false;
+            int lo = r0, hi = rows;                       // largest r1 with cum[r1] - cum[r0] <= room
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (cum[mid] - cum[r0] <= room) lo = mid; else hi = mid - 1;
+            }
+            if (lo == r0) return false;                   // not even one row fits
+            r0 = lo;
+        }
+        if (out) out[parts] = rows;
+        return r0 >= rows;
+    };
+    long double lo = 0, hi = cum[rows] + fixed(0) + 1;
+    for (int it = 0; it < 60; ++it) {
+        const long double mid = (lo + hi) / 2;
+        if (greedy(mid, nullptr)) hi = mid; else lo = mid;
+    }
+    if (!greedy(hi, bounds)) partition_costs(c, rows, parts, bounds);      // cannot happen; keep a valid answer
+    bounds[parts] = rows;
+}
+
 }  // namespace sbh
 
 static int check_csr_args(int rows, int cols, const int32_t* ptr, const char* name) {
@@ -1430,6 +1466,21 @@ int spgemm_b200_row_costs(const spgemm_b200_mat* a, const spgemm_b200_mat* b, co
     if (!d_costs) dfree(costs);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(SPGEMM_B200_ERR_CUDA, "row_costs", e);
+    return SPGEMM_B200_OK;
+}
+
+int spgemm_b200_partition_tail(const int64_t* d_costs, const int32_t* indptr_host, double tail_coeff, int rows, int parts,
+                               int32_t* bounds_host) {
+    if (!d_costs || !indptr_host || !bounds_host || rows < 0 || parts <= 0)
+        return fail(SPGEMM_B200_ERR_ARG, "partition_tail: bad argument");
+    ENTER_DEFAULT();
+    std::vector<int64_t> c((size_t)rows), tail((size_t)rows + 1);
+    if (rows) {
+        CU(cudaMemcpyAsync(c.data(), d_costs, (size_t)rows * 8, cudaMemcpyDeviceToHost, cx().stream));
+        CU(cudaStreamSynchronize(cx().stream));
+    }
+    for (int i = 0; i <= rows; ++i) tail[i] = (int64_t)indptr_host[rows] - indptr_host[i];
+    partition_costs_tail(c.data(), tail.data(), tail_coeff, rows, parts, bounds_host);
     return SPGEMM_B200_OK;
 }
 

@@ -139,6 +139,9 @@ int triple_rows(const spgemm_b200_mat* h, const spgemm_b200_mat* q, const spgemm
 int row_costs_impl(const spgemm_b200_mat* a, const spgemm_b200_mat* b, const spgemm_b200_mat* q, int upper_only,
                    int dense_cols, int64_t* d_costs);
 void partition_costs(const int64_t* costs, int rows, int parts, int32_t* bounds);
+// the same with a fixed cost per block that depends on its first row: tail_coeff * tail[first row]
+void partition_costs_tail(const int64_t* costs, const int64_t* tail, double tail_coeff, int rows, int parts, int32_t* bounds);
+constexpr double kTripleTailCoeff = 8.6;      // cost units per entry of H a rank has to transpose (k_triple_costs units)
 // rows [r0, r1) of an n-column result whose entries left of the diagonal are zero: columns [block start, n) of
 // each fixed row block cross PCIe (asynchronous, on the context's stream).  d_c holds the rows [r0, r1) only.
 cudaError_t d2h_upper_rows(const double* d_c, int n, int r0, int r1, double* c_host);

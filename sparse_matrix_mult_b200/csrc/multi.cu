@@ -247,7 +247,15 @@ void worker(Job* job, int d) {
             if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
             if (e != cudaSuccess) rc = fail(SPGEMM_B200_ERR_CUDA, "multi: row costs copy", e);
         }
-        if (!rc) partition_costs(costs.data(), m, job->n_gpus, job->bounds.data());
+        if (!rc) {
+            if (job->kind == K_TRIPLE) {                      // the rank that starts at row r transposes rows r.. of H
+                std::vector<int64_t> tail((size_t)m + 1);
+                for (int i = 0; i <= m; ++i) tail[i] = (int64_t)job->a.ptr[m] - job->a.ptr[i];
+                partition_costs_tail(costs.data(), tail.data(), kTripleTailCoeff, m, job->n_gpus, job->bounds.data());
+            } else {
+                partition_costs(costs.data(), m, job->n_gpus, job->bounds.data());
+            }
+        }
         dfree(d_costs);
     }
     mark(EV_ANALYSIS);

@@ -270,9 +270,20 @@ def row_costs(a, b, q=None, upper_only=False, dense_cols=0):
     return d, int(total.value)
 
 
-def partition_rows(d_costs, rows, parts):
-    """Flop-balanced contiguous row bounds (len parts+1) -- the multi-GPU replacement of limits()."""
+TRIPLE_TAIL_COEFF = 8.6      # SPGEMM_B200_TRIPLE_TAIL_COEFF (include/spgemm_b200.h)
+
+
+def partition_rows(d_costs, rows, parts, tail_indptr=None, tail_coeff=TRIPLE_TAIL_COEFF):
+    """Cost-balanced contiguous row bounds (len parts+1) -- the multi-GPU replacement of limits().  tail_indptr (the
+    host row pointers of H) selects the triple-product variant, where the block that starts at row r also pays for
+    transposing rows r.. of H."""
     out = np.zeros(parts + 1, dtype=np.int32)
-    _check(matrix_ops.get_lib().spgemm_b200_partition(_vp(d_costs), int(rows), int(parts),
-                                                      out.ctypes.data_as(_i32p)), "spgemm_b200_partition")
+    lib = matrix_ops.get_lib()
+    if tail_indptr is not None:
+        ptr = np.ascontiguousarray(tail_indptr, dtype=np.int32)
+        _check(lib.spgemm_b200_partition_tail(_vp(d_costs), ptr.ctypes.data_as(_i32p), float(tail_coeff), int(rows),
+                                              int(parts), out.ctypes.data_as(_i32p)), "spgemm_b200_partition_tail")
+    else:
+        _check(lib.spgemm_b200_partition(_vp(d_costs), int(rows), int(parts), out.ctypes.data_as(_i32p)),
+               "spgemm_b200_partition")
     return out

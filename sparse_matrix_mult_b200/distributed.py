@@ -252,7 +252,8 @@ def cuda_partition(a_t, b_t, kind, upper_only, world):
         costs, _ = dev.row_costs(A, Ht, B, upper_only)
     else:
         costs, _ = dev.row_costs(A, B, None, upper_only, dense_cols=(b_t[0][1] if kind == "dense" else 0))
-    bounds = dev.partition_rows(costs, a_t[0][0], world)
+    bounds = dev.partition_rows(costs, a_t[0][0], world,
+                                tail_indptr=a_t[1].cpu().numpy() if kind == "triple" else None)
     matrix_ops.get_lib().spgemm_b200_device_free(costs)
     return bounds.astype(np.int64)
 

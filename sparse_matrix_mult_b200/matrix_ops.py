@@ -111,6 +111,7 @@ class MatrixOpsLibrary:
         L.spgemm_b200_symmetrize_dev.argtypes = [_vp, ctypes.c_int]
         L.spgemm_b200_row_costs.argtypes = [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_int64)]
         L.spgemm_b200_partition.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _i32p]
+        L.spgemm_b200_partition_tail.argtypes = [_vp, _i32p, ctypes.c_double, ctypes.c_int, ctypes.c_int, _i32p]
         L.spgemm_b200_device_alloc.argtypes = [ctypes.c_size_t]
         L.spgemm_b200_device_alloc.restype = _vp
         L.spgemm_b200_device_free.argtypes = [_vp]

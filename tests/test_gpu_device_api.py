@@ -367,3 +367,49 @@ def test_triple_cached_transpose():
     out = dev.triple_product(H, Q, None, True, 0, 400)
     np.testing.assert_allclose(out.to_host(), want, rtol=1e-12, atol=1e-14)
     out.free()
+
+
+# ---- partition with a start-dependent fixed cost (triple product over several GPUs) ------------------------
+def _block_cost(costs, tail, coeff, r0, r1):
+    return (coeff * tail[r0] if r1 > r0 else 0.0) + float(np.sum(costs[r0:r1] + 1))
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_partition_tail_minimises_the_largest_block(parts):
+    """spgemm_b200_partition_tail: bounds cover the rows, and no neighbouring single-row shift of one cut lowers
+    the largest block cost (block cost = coeff * entries of H from its first row on + its rows' costs); with
+    coeff = 0 the largest block is no worse than that of the equal-sum partition."""
+    w = synthetic.workload("cfg3s")
+    h, q = w["a"], w["b"]
+    H, Q = dev.DeviceMatrix.from_scipy(h), dev.DeviceMatrix.from_scipy(q)
+    Ht = H.transpose()
+    d_costs, total = dev.row_costs(H, Ht, Q, upper_only=True)
+    n = h.shape[0]
+    costs = np.zeros(n, dtype=np.int64)
+    dev.copy_to_host(costs, d_costs)
+    assert int(costs.sum()) == total
+    tail = (h.indptr[-1] - h.indptr).astype(np.float64)
+    for coeff in (0.0, 8.6, 500.0):
+        b = dev.partition_rows(d_costs, n, parts, tail_indptr=h.indptr, tail_coeff=coeff)
+        assert b[0] == 0 and b[-1] == n and np.all(np.diff(b) >= 0)
+        worst = max(_block_cost(costs, tail, coeff, b[p], b[p + 1]) for p in range(parts))
+        # greedy bottleneck: the bound is tight to one row -- removing the last row of the worst block's predecessors
+        # cannot help, so compare with every partition that moves ONE cut by one row
+        for p in range(1, parts):
+            for step in (-1, 1):
+                c = b.copy()
+                c[p] += step
+                if c[p] < c[p - 1] or c[p] > c[p + 1]:
+                    continue
+                alt = max(_block_cost(costs, tail, coeff, c[k], c[k + 1]) for k in range(parts))
+                assert alt >= worst - max(costs.max() + 1, 1)
+        if coeff == 0.0:
+            e = dev.partition_rows(d_costs, n, parts)
+            even = max(_block_cost(costs, tail, 0.0, e[p], e[p + 1]) for p in range(parts))
+            assert worst <= even
+        if coeff == 500.0 and parts > 1:
+            e = dev.partition_rows(d_costs, n, parts)
+            assert b[1] <= e[1]            # the first block pays the whole transpose, so it gets fewer rows
+    matrix_ops.get_lib().spgemm_b200_device_free(d_costs)
+    for x in (Ht, H, Q):
+        x.free()
