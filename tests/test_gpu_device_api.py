@@ -413,3 +413,48 @@ def test_partition_tail_minimises_the_largest_block(parts):
     matrix_ops.get_lib().spgemm_b200_device_free(d_costs)
     for x in (Ht, H, Q):
         x.free()
+
+
+# ---- banded-Q kernel: stream pipeline across ranges, empty rows of Q ---------------------------------------
+def _drop_rows(q, rows):
+    """Q with the given rows emptied (still one run of consecutive columns per non-empty row)."""
+    q = q.tolil()
+    for r in rows:
+        q[r, :] = 0
+    q = q.tocsr()
+    q.eliminate_zeros()
+    q.sort_indices()
+    return q
+
+
+@pytest.mark.parametrize("pipe", [1, 2])
+@pytest.mark.parametrize("half_width,h_density", [(0, 0.02), (2, 0.002), (2, 0.02), (20, 0.002), (20, 0.02),
+                                                  (120, 0.004)])
+def test_triple_runs_kernel_short_ranges_and_empty_q_rows(pipe, half_width, h_density, monkeypatch):
+    """k_triple_runs: ranges of H^T of 0, 1, 2 and many 32-entry steps (the stream pipeline runs two steps ahead,
+    across range boundaries), runs longer than one weight-table pass, and rows of Q with no entries at all -- an entry
+    of H that points at one contributes nothing and must not disturb the entries its warp takes next."""
+    monkeypatch.setenv("SPGEMM_B200_TRIPLE_PIPE", str(pipe))
+    rng = np.random.default_rng(100 * half_width + pipe)
+    n, k = 260, 3000
+    h = sp.random(n, k, density=h_density, format='csr', random_state=rng)
+    h.sort_indices()
+    q = synthetic.banded_cov(k, half_width=half_width, length=7.0)
+    # empty every 7th row of Q and the rows the first entries of rows 0..39 of H point at
+    drop = set(range(3, k, 7))
+    for i in range(40):
+        if h.indptr[i + 1] > h.indptr[i]:
+            drop.add(int(h.indices[h.indptr[i]]))
+    q = _drop_rows(q, sorted(drop))
+    assert (np.diff(q.indptr) == 0).sum() >= len(drop)
+    want = port.triple_product(h, q, 0)
+    got = sparse_matrix_multiply(h, q, use_triple_product=True)
+    assert_dense_equal(got, want, f"runs kernel pipe={pipe} hw={half_width}")
+    # the full (non-symmetric) product through the device API takes the unfiltered loop in every panel
+    H, Q = dev.DeviceMatrix.from_scipy(h), dev.DeviceMatrix.from_scipy(q)
+    full = (h @ q @ h.T).toarray()
+    out = dev.triple_product(H, Q, None, False, 0, n)
+    np.testing.assert_allclose(out.to_host(), full, rtol=1e-12, atol=1e-13)
+    out.free()
+    H.free()
+    Q.free()
