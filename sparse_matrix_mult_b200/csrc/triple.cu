@@ -327,9 +327,7 @@ __device__ __forceinline__ double ld_keep_f64(const double* p, unsigned long lon
     return v;
 }
 
-struct RunStep { int2 kc; double v; };          // one entry of the stream per lane; kc.x < 0: none
-
-template <bool UPPER, int PIPE>
+template <bool UPPER>
 __global__ void __launch_bounds__(1024, 1)
 k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __restrict__ t_kc,
               const double* __restrict__ t_val, TriplePlan plan, int row_begin, int nrows, int win_cap,
@@ -405,143 +403,67 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
                 }
             };
             prefetch(e);
-            if constexpr (PIPE >= 2) {
-                // The ranges of this warp's entries of H are walked as ONE stream, 32 entries per step, with the loads
-                // of the two steps after the current one in flight -- across range boundaries: the bounds of the next
-                // entry's range are prefetched at the start of the current one, so its first two steps are loaded
-                // while the current range is still being added (PIPE 1 restarted the pipeline at every range: one
-                // exposed L2 / DRAM latency per ~170 entries).
-                auto load_at = [&](int x, int end) {
-                    RunStep o;
-                    o.kc = make_int2(-1, 0);
-                    o.v = 0.0;
-                    if (x < end) {
-                        o.kc = ld_keep_i2(t_kc + x, keep);
-                        o.v = ld_keep_f64(t_val + x, keep);
+            for (; e < cnt; e += nwarp) {
+                const int len = s_len[e], qs = s_qs[e], c0 = s_c0[e];
+                const double hv = s_hv[e];
+                for (int t0 = 0; t0 < len; t0 += kRunPiece) {
+                    const int cn = min(kRunPiece, len - t0);
+                    const int cb = c0 + t0;
+                    double q0, q1, q2;
+                    int es, ee;
+                    if (t0 == 0) { q0 = nq0; q1 = nq1; q2 = nq2; es = nes; ee = nee; }
+                    else {
+                        q0 = lane < cn ? __ldcs(Q.val + qs + t0 + lane) : 0.0;
+                        q1 = lane + 32 < cn ? __ldcs(Q.val + qs + t0 + lane + 32) : 0.0;
+                        q2 = lane + 64 < cn ? __ldcs(Q.val + qs + t0 + lane + 64) : 0.0;
+                        es = ld_keep_i32(hp + cb, keep);
+                        ee = ld_keep_i32(hp + cb + cn, keep);
                     }
-                    return o;
-                };
-                RunStep s0 = load_at(nes + lane, nee), s1 = load_at(nes + 32 + lane, nee);
-                for (; e < cnt; e += nwarp) {
-                    const int len = s_len[e], qs = s_qs[e], c0 = s_c0[e];
-                    const double hv = s_hv[e];
-                    if (len <= 0) {                            // empty row of Q: restart the stream at the next entry
-                        prefetch(e + nwarp);
-                        s0 = load_at(nes + lane, nee);
-                        s1 = load_at(nes + 32 + lane, nee);
-                        continue;
-                    }
-                    for (int t0 = 0; t0 < len; t0 += kRunPiece) {
-                        const int cn = min(kRunPiece, len - t0);
-                        const int cb = c0 + t0;
-                        const bool last_piece = t0 + kRunPiece >= len;
-                        double q0, q1, q2;
-                        int es, ee;
-                        if (t0 == 0) { q0 = nq0; q1 = nq1; q2 = nq2; es = nes; ee = nee; }   // s0, s1: its first two steps
-                        else {
-                            q0 = lane < cn ? __ldcs(Q.val + qs + t0 + lane) : 0.0;
-                            q1 = lane + 32 < cn ? __ldcs(Q.val + qs + t0 + lane + 32) : 0.0;
-                            q2 = lane + 64 < cn ? __ldcs(Q.val + qs + t0 + lane + 64) : 0.0;
-                            es = ld_keep_i32(hp + cb, keep);
-                            ee = ld_keep_i32(hp + cb + cn, keep);
-                            s0 = load_at(es + lane, ee);
-                            s1 = load_at(es + 32 + lane, ee);
+                    if (t0 + kRunPiece >= len) prefetch(e + nwarp);   // last piece of this run: start the next entry's loads
+                    s_wt[lane] = hv * q0;
+                    s_wt[lane + 32] = hv * q1;
+                    s_wt[lane + 64] = hv * q2;
+                    __syncwarp();
+                    const double* wt = s_wt - cb;              // weight of column c: wt[c]
+                    // the range [es, ee), 32 entries per step, as a rolling pipeline: the (k, c) pairs and values of the
+                    // next step are in flight while the current step is multiplied and added (ranges are ~100-200
+                    // entries long: wider steps would leave most lanes of the last one idle)
+                    int x = es + lane;
+                    const int2* pk = t_kc + x;
+                    const double* pv = t_val + x;
+                    int2 kc = x < ee ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
+                    double v = x < ee ? ld_keep_f64(pv, keep) : 0.0;
+                    if (!filtered) {
+                        for (; x < ee; x += 32) {
+                            pk += 32;
+                            pv += 32;
+                            const bool more = x + 32 < ee;
+                            const int2 kcn = more ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
+                            const double vn = more ? ld_keep_f64(pv, keep) : 0.0;
+                            atomicAdd(acc + (kc.x - lo), wt[kc.y] * v);
+                            kc = kcn;
+                            v = vn;
                         }
-                        if (last_piece) prefetch(e + nwarp);   // nes, nee, nq*: the NEXT entry from here on
-                        s_wt[lane] = hv * q0;
-                        s_wt[lane + 32] = hv * q1;
-                        s_wt[lane + 64] = hv * q2;
-                        __syncwarp();
-                        const double* wt = s_wt - cb;
-                        const int steps = (ee - es + 31) >> 5;
-                        // ranges shorter than the pipeline: the head of the next range belongs into s0 / s1 already
-                        if (last_piece && steps < 2) {
-                            if (steps == 0) {
-                                s0 = load_at(nes + lane, nee);
-                                s1 = load_at(nes + 32 + lane, nee);
-                            } else {
-                                s1 = load_at(nes + lane, nee);
-                            }
-                        }
-                        for (int st = 0; st < steps; ++st) {
-                            const int t = st + 2;              // the step loaded now: of this range, or of the next one
-                            RunStep sn;
-                            if (t < steps) sn = load_at(es + 32 * t + lane, ee);
-                            else if (last_piece) sn = load_at(nes + 32 * (t - steps) + lane, nee);
-                            else { sn.kc = make_int2(-1, 0); sn.v = 0.0; }
-                            if (filtered ? s0.kc.x >= lo : s0.kc.x >= 0) {
-                                atomicAdd(acc + (s0.kc.x - lo), wt[s0.kc.y] * s0.v);
-                                if (filtered) ++p2;
-                            }
-                            s0 = s1;
-                            s1 = sn;
-                        }
-                        if (!filtered && lane == 0) p2 += (unsigned)(ee - es);
-                        __syncwarp();                          // the table is rewritten by the next piece
-                    }
-                }
-            } else {
-                for (; e < cnt; e += nwarp) {
-                    const int len = s_len[e], qs = s_qs[e], c0 = s_c0[e];
-                    const double hv = s_hv[e];
-                    for (int t0 = 0; t0 < len; t0 += kRunPiece) {
-                        const int cn = min(kRunPiece, len - t0);
-                        const int cb = c0 + t0;
-                        double q0, q1, q2;
-                        int es, ee;
-                        if (t0 == 0) { q0 = nq0; q1 = nq1; q2 = nq2; es = nes; ee = nee; }
-                        else {
-                            q0 = lane < cn ? __ldcs(Q.val + qs + t0 + lane) : 0.0;
-                            q1 = lane + 32 < cn ? __ldcs(Q.val + qs + t0 + lane + 32) : 0.0;
-                            q2 = lane + 64 < cn ? __ldcs(Q.val + qs + t0 + lane + 64) : 0.0;
-                            es = ld_keep_i32(hp + cb, keep);
-                            ee = ld_keep_i32(hp + cb + cn, keep);
-                        }
-                        if (t0 + kRunPiece >= len) prefetch(e + nwarp);   // last piece of this run: start the next entry's loads
-                        s_wt[lane] = hv * q0;
-                        s_wt[lane + 32] = hv * q1;
-                        s_wt[lane + 64] = hv * q2;
-                        __syncwarp();
-                        const double* wt = s_wt - cb;              // weight of column c: wt[c]
-                        // the range [es, ee), 32 entries per step, as a rolling pipeline: the (k, c) pairs and values of the
-                        // next step are in flight while the current step is multiplied and added (ranges are ~100-200
-                        // entries long: wider steps would leave most lanes of the last one idle)
-                        int x = es + lane;
-                        const int2* pk = t_kc + x;
-                        const double* pv = t_val + x;
-                        int2 kc = x < ee ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
-                        double v = x < ee ? ld_keep_f64(pv, keep) : 0.0;
-                        if (!filtered) {
-                            for (; x < ee; x += 32) {
-                                pk += 32;
-                                pv += 32;
-                                const bool more = x + 32 < ee;
-                                const int2 kcn = more ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
-                                const double vn = more ? ld_keep_f64(pv, keep) : 0.0;
+                        if (lane == 0) p2 += (unsigned)(ee - es);
+                    } else {
+                        for (; x < ee; x += 32) {
+                            pk += 32;
+                            pv += 32;
+                            const bool more = x + 32 < ee;
+                            const int2 kcn = more ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
+                            const double vn = more ? ld_keep_f64(pv, keep) : 0.0;
+                            if (kc.x >= lo) {
                                 atomicAdd(acc + (kc.x - lo), wt[kc.y] * v);
-                                kc = kcn;
-                                v = vn;
+                                ++p2;
                             }
-                            if (lane == 0) p2 += (unsigned)(ee - es);
-                        } else {
-                            for (; x < ee; x += 32) {
-                                pk += 32;
-                                pv += 32;
-                                const bool more = x + 32 < ee;
-                                const int2 kcn = more ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
-                                const double vn = more ? ld_keep_f64(pv, keep) : 0.0;
-                                if (kc.x >= lo) {
-                                    atomicAdd(acc + (kc.x - lo), wt[kc.y] * v);
-                                    ++p2;
-                                }
-                                kc = kcn;
-                                v = vn;
-                            }
+                            kc = kcn;
+                            v = vn;
                         }
-                        __syncwarp();                          // the table is rewritten by the next piece
                     }
-                    if (len <= 0) prefetch(e + nwarp);         // empty row of Q: nothing to stream, keep the pipeline fed
+                    __syncwarp();                          // the table is rewritten by the next piece
                 }
+                if (len <= 0) prefetch(e + nwarp);         // empty row of Q: nothing to stream, but the next entry's
+                                                           // loads must still be started (its first piece reads them)
             }
             __syncthreads();                               // tables are rewritten by the next slice / item
         }
@@ -582,13 +504,9 @@ cudaError_t triple_kernels_configure() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_triple_panels<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_triple_runs<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    e = cudaFuncSetAttribute(k_triple_runs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_triple_runs<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_triple_runs<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_triple_runs<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    return cudaFuncSetAttribute(k_triple_runs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -652,15 +570,10 @@ cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q
     if (grid < 1) grid = 1;
     const size_t smem = smem_of(threads);
     if (q_runs) {
-        const bool pipe2 = env_int("SPGEMM_B200_TRIPLE_PIPE", 2) >= 2;
-        if (upper_only && pipe2)
-            k_triple_runs<true, 2><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
-        else if (upper_only)
-            k_triple_runs<true, 1><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
-        else if (pipe2)
-            k_triple_runs<false, 2><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
+        if (upper_only)
+            k_triple_runs<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
         else
-            k_triple_runs<false, 1><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
+            k_triple_runs<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
     } else {
         if (upper_only)
             k_triple_panels<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);

@@ -427,15 +427,13 @@ def _drop_rows(q, rows):
     return q
 
 
-@pytest.mark.parametrize("pipe", [1, 2])
 @pytest.mark.parametrize("half_width,h_density", [(0, 0.02), (2, 0.002), (2, 0.02), (20, 0.002), (20, 0.02),
                                                   (120, 0.004)])
-def test_triple_runs_kernel_short_ranges_and_empty_q_rows(pipe, half_width, h_density, monkeypatch):
-    """k_triple_runs: ranges of H^T of 0, 1, 2 and many 32-entry steps (the stream pipeline runs two steps ahead,
-    across range boundaries), runs longer than one weight-table pass, and rows of Q with no entries at all -- an entry
-    of H that points at one contributes nothing and must not disturb the entries its warp takes next."""
-    monkeypatch.setenv("SPGEMM_B200_TRIPLE_PIPE", str(pipe))
-    rng = np.random.default_rng(100 * half_width + pipe)
+def test_triple_runs_kernel_short_ranges_and_empty_q_rows(half_width, h_density):
+    """k_triple_runs: ranges of H^T of 0, 1, 2 and many 32-entry steps, runs longer than one weight-table pass, and
+    rows of Q with no entries at all -- an entry of H that points at one contributes nothing and must not disturb the
+    entry its warp takes next (whose prefetched loads it used to skip: the first 96 products of that entry were lost)."""
+    rng = np.random.default_rng(100 * half_width + 1)
     n, k = 260, 3000
     h = sp.random(n, k, density=h_density, format='csr', random_state=rng)
     h.sort_indices()
@@ -449,7 +447,7 @@ def test_triple_runs_kernel_short_ranges_and_empty_q_rows(pipe, half_width, h_de
     assert (np.diff(q.indptr) == 0).sum() >= len(drop)
     want = port.triple_product(h, q, 0)
     got = sparse_matrix_multiply(h, q, use_triple_product=True)
-    assert_dense_equal(got, want, f"runs kernel pipe={pipe} hw={half_width}")
+    assert_dense_equal(got, want, f"runs kernel hw={half_width}")
     # the full (non-symmetric) product through the device API takes the unfiltered loop in every panel
     H, Q = dev.DeviceMatrix.from_scipy(h), dev.DeviceMatrix.from_scipy(q)
     full = (h @ q @ h.T).toarray()
