@@ -1,0 +1,126 @@
+"""Seeded structure fuzz of the CUDA path against the oracle (GPU): many small operands whose STRUCTURE is adversarial --
+empty matrices, empty rows and columns, single rows, dimensions on either side of the warp / bin boundaries, dense
+blocks next to empty ones, hub columns, banded Q with emptied rows, Q with runs longer than the weight table -- through
+all the modes of sparse_matrix_multiply (/root/reference/sparse_matrix_mult/matrix_ops.py:253-397).  Values are
+compared to rtol 1e-12, structure bit-exactly after sorting (helpers.py).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import assert_csr_equal, assert_dense_equal
+from oracle import port
+from sparse_matrix_mult_b200 import device as dev
+from sparse_matrix_mult_b200 import sparse_matrix_multiply
+
+pytestmark = pytest.mark.gpu
+
+_DIMS = [1, 2, 3, 31, 32, 33, 63, 64, 65, 100, 127, 128, 129, 257, 400]
+_DENS = [0.0, 0.002, 0.02, 0.2, 0.9]
+
+
+def _shape_up(x, rng):
+    """Knock structure into a random matrix: empty rows, empty columns, one dense row, one hub column."""
+    x = x.tolil()
+    m, n = x.shape
+    what = rng.integers(0, 6)
+    if what == 0 and m > 2:                               # a third of the rows empty
+        for r in rng.choice(m, size=m // 3, replace=False):
+            x[int(r), :] = 0
+    elif what == 1 and n > 2:                             # a third of the columns empty
+        for c in rng.choice(n, size=n // 3, replace=False):
+            x[:, int(c)] = 0
+    elif what == 2:                                       # one dense row
+        x[int(rng.integers(0, m)), :] = rng.random(n) + 0.5
+    elif what == 3:                                       # hub column
+        x[:, int(rng.integers(0, n))] = (rng.random(m) + 0.5).reshape(-1, 1)
+    elif what == 4 and m > 1:                             # the last rows empty (trailing empty rows in indptr)
+        x[m - max(1, m // 4):, :] = 0
+    x = x.tocsr()
+    x.eliminate_zeros()
+    x.sort_indices()
+    x.indices = x.indices.astype(np.int32)
+    x.indptr = x.indptr.astype(np.int32)
+    return x
+
+
+def _random(m, n, rng):
+    x = sp.random(m, n, density=float(rng.choice(_DENS)), format='csr', random_state=rng, dtype=np.float64)
+    return _shape_up(x, rng)
+
+
+def _dims(rng, count):
+    return [int(rng.choice(_DIMS)) for _ in range(count)]
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_products(seed):
+    rng = np.random.default_rng(1000 + seed)
+    m, k, n = _dims(rng, 3)
+    if seed % 2:
+        n = m                                             # square result: the symmetric variants apply
+    a, b = _random(m, k, rng), _random(k, n, rng)
+    assert_csr_equal(sparse_matrix_multiply(a, b), port.spgemm_csr(a, b), f"sparse {m}x{k}x{n}")
+    assert_dense_equal(sparse_matrix_multiply(a, b, output_format='dense'), port.spgemm_dense(a, b), f"dense {m}x{k}x{n}")
+    if m == n:
+        assert_csr_equal(sparse_matrix_multiply(a, b, symmetric=True), port.spgemm_csr(a, b, True), "sparse_sym")
+        assert_dense_equal(sparse_matrix_multiply(a, b, output_format='dense', symmetric=True),
+                           port.spgemm_dense(a, b, True), "dense_sym")
+
+
+def _q_for(k, rng):
+    kind = int(rng.integers(0, 5))
+    if kind == 0:                                         # banded, possibly wider than the weight table (96)
+        hw = int(rng.choice([0, 1, 5, 40, 110]))
+        hw = min(hw, max(0, k - 1))
+        offs = list(range(-hw, hw + 1))
+        q = sp.diags([np.full(k - abs(o), np.exp(-abs(o) / 9.0)) for o in offs], offs, format='csr', dtype=np.float64)
+    elif kind == 1:                                       # banded with emptied rows
+        hw = min(int(rng.choice([1, 3, 20])), max(0, k - 1))
+        offs = list(range(-hw, hw + 1))
+        q = sp.diags([np.full(k - abs(o), 1.0 / (1 + abs(o))) for o in offs], offs, format='lil', dtype=np.float64)
+        for r in rng.choice(k, size=max(1, k // 4), replace=False):
+            q[int(r), :] = 0
+        q = q.tocsr()
+    elif kind == 2:                                       # general sparse
+        q = sp.random(k, k, density=float(rng.choice([0.002, 0.05, 0.5])), format='csr', random_state=rng)
+    elif kind == 3:                                       # empty
+        q = sp.csr_matrix((k, k), dtype=np.float64)
+    else:                                                 # one run per row, at random places and of random lengths
+        rows, cols = [], []
+        for r in range(k):
+            ln = int(rng.integers(0, min(k, 130) + 1))
+            c0 = int(rng.integers(0, k - ln + 1))
+            rows += [r] * ln
+            cols += list(range(c0, c0 + ln))
+        q = sp.csr_matrix((rng.random(len(rows)) + 0.1, (rows, cols)), shape=(k, k))
+    q.eliminate_zeros()
+    q.sort_indices()
+    q.indices = q.indices.astype(np.int32)
+    q.indptr = q.indptr.astype(np.int32)
+    return q
+
+
+@pytest.mark.parametrize("seed", range(50))
+def test_fuzz_triple_product(seed):
+    rng = np.random.default_rng(5000 + seed)
+    n, k = _dims(rng, 2)
+    if seed % 5 == 0:
+        k = int(rng.choice([700, 1500, 3000]))            # long H rows: more entries than warps, ranges of many steps
+    h = _random(n, k, rng)
+    q = _q_for(k, rng)
+    what = f"triple n={n} k={k} nnz(H)={h.nnz} nnz(Q)={q.nnz}"
+    assert_dense_equal(sparse_matrix_multiply(h, q, use_triple_product=True), port.triple_product(h, q, 0), what)
+    assert_dense_equal(sparse_matrix_multiply(h, q, use_triple_product=True, compute_full_matrix=1),
+                       port.triple_product(h, q, 1), what + " full")
+    # row ranges through the device API, full (unfiltered) product
+    H, Q = dev.DeviceMatrix.from_scipy(h), dev.DeviceMatrix.from_scipy(q)
+    full = (h @ q @ h.T).toarray()
+    cut = n // 2
+    for r0, r1 in ((0, cut), (cut, n)):
+        if r1 > r0:
+            out = dev.triple_product(H, Q, None, False, r0, r1)
+            np.testing.assert_allclose(out.to_host(), full[r0:r1], rtol=1e-12, atol=1e-13, err_msg=what)
+            out.free()
+    H.free()
+    Q.free()
