@@ -66,6 +66,17 @@ def test_fuzz_products(seed):
         assert_csr_equal(sparse_matrix_multiply(a, b, symmetric=True), port.spgemm_csr(a, b, True), "sparse_sym")
         assert_dense_equal(sparse_matrix_multiply(a, b, output_format='dense', symmetric=True),
                            port.spgemm_dense(a, b, True), "dense_sym")
+    # the kernels themselves through the device API (no host short-circuit for operands without entries)
+    A, B = dev.DeviceMatrix.from_scipy(a), dev.DeviceMatrix.from_scipy(b)
+    ref = (a @ b).toarray()
+    res = dev.spgemm_csr(A, B, False, 0, m)
+    np.testing.assert_allclose(res.to_scipy().toarray(), ref, rtol=1e-12, atol=1e-13)
+    res.free()
+    out = dev.spgemm_dense(A, B, False, 0, m)
+    np.testing.assert_allclose(out.to_host(), ref, rtol=1e-12, atol=1e-13)
+    out.free()
+    A.free()
+    B.free()
 
 
 def _q_for(k, rng):
@@ -110,10 +121,18 @@ def test_fuzz_triple_product(seed):
     h = _random(n, k, rng)
     q = _q_for(k, rng)
     what = f"triple n={n} k={k} nnz(H)={h.nnz} nnz(Q)={q.nnz}"
-    assert_dense_equal(sparse_matrix_multiply(h, q, use_triple_product=True), port.triple_product(h, q, 0), what)
-    assert_dense_equal(sparse_matrix_multiply(h, q, use_triple_product=True, compute_full_matrix=1),
-                       port.triple_product(h, q, 1), what + " full")
-    # row ranges through the device API, full (unfiltered) product
+    # the entry point, against the oracle's restatement of it: an operand without entries short-circuits to an empty
+    # (n x k) result whatever the mode (matrix_ops.py:315-319), which the drop-in reproduces
+    for kwargs in (dict(), dict(compute_full_matrix=1)):
+        got = sparse_matrix_multiply(h, q, use_triple_product=True, **kwargs)
+        want = port.sparse_matrix_multiply(h, q, use_triple_product=True, **kwargs)
+        if sp.issparse(want):
+            assert sp.issparse(got)
+            assert_csr_equal(got, want, what)
+        else:
+            assert_dense_equal(got, want, what + str(kwargs))
+    # the kernels themselves, empty operands included: row ranges through the device API, full (unfiltered) product
+    # and the upper triangle
     H, Q = dev.DeviceMatrix.from_scipy(h), dev.DeviceMatrix.from_scipy(q)
     full = (h @ q @ h.T).toarray()
     cut = n // 2
@@ -121,6 +140,9 @@ def test_fuzz_triple_product(seed):
         if r1 > r0:
             out = dev.triple_product(H, Q, None, False, r0, r1)
             np.testing.assert_allclose(out.to_host(), full[r0:r1], rtol=1e-12, atol=1e-13, err_msg=what)
+            out.free()
+            out = dev.triple_product(H, Q, None, True, r0, r1)
+            np.testing.assert_allclose(out.to_host(), np.triu(full)[r0:r1], rtol=1e-12, atol=1e-13, err_msg=what + " upper")
             out.free()
     H.free()
     Q.free()
