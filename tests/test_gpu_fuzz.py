@@ -21,22 +21,32 @@ _DENS = [0.0, 0.002, 0.02, 0.2, 0.9]
 
 def _shape_up(x, rng):
     """Knock structure into a random matrix: empty rows, empty columns, one dense row, one hub column."""
-    x = x.tolil()
+    x = x.tocoo()
     m, n = x.shape
+    row, col, val = x.row, x.col, x.data
     what = rng.integers(0, 6)
     if what == 0 and m > 2:                               # a third of the rows empty
-        for r in rng.choice(m, size=m // 3, replace=False):
-            x[int(r), :] = 0
+        keep = ~np.isin(row, rng.choice(m, size=m // 3, replace=False))
+        row, col, val = row[keep], col[keep], val[keep]
     elif what == 1 and n > 2:                             # a third of the columns empty
-        for c in rng.choice(n, size=n // 3, replace=False):
-            x[:, int(c)] = 0
+        keep = ~np.isin(col, rng.choice(n, size=n // 3, replace=False))
+        row, col, val = row[keep], col[keep], val[keep]
     elif what == 2:                                       # one dense row
-        x[int(rng.integers(0, m)), :] = rng.random(n) + 0.5
+        r = int(rng.integers(0, m))
+        keep = row != r
+        row = np.concatenate([row[keep], np.full(n, r)])
+        col = np.concatenate([col[keep], np.arange(n)])
+        val = np.concatenate([val[keep], rng.random(n) + 0.5])
     elif what == 3:                                       # hub column
-        x[:, int(rng.integers(0, n))] = (rng.random(m) + 0.5).reshape(-1, 1)
+        c = int(rng.integers(0, n))
+        keep = col != c
+        row = np.concatenate([row[keep], np.arange(m)])
+        col = np.concatenate([col[keep], np.full(m, c)])
+        val = np.concatenate([val[keep], rng.random(m) + 0.5])
     elif what == 4 and m > 1:                             # the last rows empty (trailing empty rows in indptr)
-        x[m - max(1, m // 4):, :] = 0
-    x = x.tocsr()
+        keep = row < m - max(1, m // 4)
+        row, col, val = row[keep], col[keep], val[keep]
+    x = sp.csr_matrix((val, (row, col)), shape=(m, n), dtype=np.float64)
     x.eliminate_zeros()
     x.sort_indices()
     x.indices = x.indices.astype(np.int32)
@@ -112,9 +122,14 @@ def _q_for(k, rng):
     return q
 
 
-@pytest.mark.parametrize("seed", range(50))
-def test_fuzz_triple_product(seed):
+@pytest.mark.parametrize("seed", range(120))
+def test_fuzz_triple_product(seed, monkeypatch):
     rng = np.random.default_rng(5000 + seed)
+    if seed >= 50:                                        # more column panels than needed / the general kernel forced
+        if seed % 3:
+            monkeypatch.setenv("SPGEMM_B200_TRIPLE_PANELS", str(1 + seed % 5))
+        if seed % 4 == 0:
+            monkeypatch.setenv("SPGEMM_B200_TRIPLE_GENERIC", "1")
     n, k = _dims(rng, 2)
     if seed % 5 == 0:
         k = int(rng.choice([700, 1500, 3000]))            # long H rows: more entries than warps, ranges of many steps
@@ -146,3 +161,44 @@ def test_fuzz_triple_product(seed):
             out.free()
     H.free()
     Q.free()
+
+
+def _shuffle_rows(x, rng):
+    """The same matrix with the entries of every row in random order (unsorted CSR)."""
+    x = x.copy()
+    for r in range(x.shape[0]):
+        s, e = x.indptr[r], x.indptr[r + 1]
+        perm = rng.permutation(e - s)
+        x.indices[s:e] = x.indices[s:e][perm]
+        x.data[s:e] = x.data[s:e][perm]
+    x.has_sorted_indices = False
+    return x
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_fuzz_products_heavier_rows(seed):
+    """Rows that land in the warp and block bins of the sparse path (hundreds to tens of thousands of products, hub
+    rows of B, a dense row of A), the symmetric cut through them, and unsorted operands (every third seed: B, or both,
+    with the entries of each row shuffled -- canonicalised on the device, same result as for the sorted operands)."""
+    rng = np.random.default_rng(9000 + seed)
+    m = int(rng.choice([300, 800, 2000]))
+    k = int(rng.choice([300, 1000, 4000]))
+    n = m if seed % 2 else int(rng.choice([500, 3000, 70000]))
+    da = float(rng.choice([0.003, 0.03, 0.2]))
+    db = float(rng.choice([0.003, 0.03, 0.2])) if n < 10000 else 0.002
+    a = _shape_up(sp.random(m, k, density=da, format='csr', random_state=rng), rng)
+    b = _shape_up(sp.random(k, n, density=db, format='csr', random_state=rng), rng)
+    a_in, b_in = a, b
+    if seed % 3 == 0:
+        b_in = _shuffle_rows(b, rng)
+        if seed % 6 == 0:
+            a_in = _shuffle_rows(a, rng)
+    what = f"{m}x{k}x{n} nnz {a.nnz} {b.nnz}"
+    assert_csr_equal(sparse_matrix_multiply(a_in, b_in), port.spgemm_csr(a, b), "sparse " + what)
+    if m == n:
+        assert_csr_equal(sparse_matrix_multiply(a_in, b_in, symmetric=True), port.spgemm_csr(a, b, True), "sparse_sym " + what)
+    if m * n <= 4_000_000:
+        assert_dense_equal(sparse_matrix_multiply(a_in, b_in, output_format='dense'), port.spgemm_dense(a, b), "dense " + what)
+        if m == n:
+            assert_dense_equal(sparse_matrix_multiply(a_in, b_in, output_format='dense', symmetric=True),
+                               port.spgemm_dense(a, b, True), "dense_sym " + what)
