@@ -202,3 +202,37 @@ def test_fuzz_products_heavier_rows(seed):
         if m == n:
             assert_dense_equal(sparse_matrix_multiply(a_in, b_in, output_format='dense', symmetric=True),
                                port.spgemm_dense(a, b, True), "dense_sym " + what)
+
+
+# ---- the same through the multi-GPU driver (csrc/multi.cu): every available GPU count; on a one-GPU box n_gpus=1 is
+# ---- forced through it.  Rows < GPUs, operands without entries in some row blocks, one-row matrices.
+def _gpu_counts():
+    from sparse_matrix_mult_b200.matrix_ops import matrix_ops
+    n = matrix_ops.get_lib().spgemm_b200_device_count()
+    return [c for c in (1, 2, 3, 4, 8) if c <= max(1, n)]
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_multi_gpu(seed, monkeypatch):
+    monkeypatch.setenv("SPGEMM_B200_FORCE_MULTI", "1")
+    rng = np.random.default_rng(7000 + seed)
+    m, k = _dims(rng, 2)
+    a = _random(m, k, rng)
+    b = _random(k, m, rng)
+    q = _q_for(k, rng)
+    for n_gpus in _gpu_counts():
+        what = f"n_gpus={n_gpus} {m}x{k} nnz {a.nnz} {b.nnz} {q.nnz}"
+        assert_csr_equal(sparse_matrix_multiply(a, b, n_gpus=n_gpus), port.sparse_matrix_multiply(a, b), "sparse " + what)
+        assert_csr_equal(sparse_matrix_multiply(a, b, symmetric=True, n_gpus=n_gpus),
+                         port.sparse_matrix_multiply(a, b, symmetric=True), "sparse_sym " + what)
+        assert_dense_equal(sparse_matrix_multiply(a, b, output_format='dense', n_gpus=n_gpus),
+                           port.sparse_matrix_multiply(a, b, output_format='dense'), "dense " + what)
+        assert_dense_equal(sparse_matrix_multiply(a, b, output_format='dense', symmetric=True, n_gpus=n_gpus),
+                           port.sparse_matrix_multiply(a, b, output_format='dense', symmetric=True), "dense_sym " + what)
+        got = sparse_matrix_multiply(a, q, use_triple_product=True, n_gpus=n_gpus)
+        want = port.sparse_matrix_multiply(a, q, use_triple_product=True)
+        if sp.issparse(want):
+            assert sp.issparse(got)
+            assert_csr_equal(got, want, "triple " + what)
+        else:
+            assert_dense_equal(got, want, "triple " + what)
