@@ -331,9 +331,12 @@ k_transpose_fill(Csr X, const int32_t* __restrict__ t_ptr, int32_t* __restrict__
 // ---------------------------------------------------------------------------------------------------
 // Paneled transpose (triple product): rows [row_begin, row_end) of X are cut into panels of `panel_w` rows and the
 // transposes of the panels are stored back to back as ONE CSR with np * X.cols rows -- row p * X.cols + c holds the
-// entries (r, x_rc) of column c with r in panel p, each stored as the pair (r, c) in t_kc next to its value.
-// t_ptr + p * X.cols is then the row-pointer array of panel p's transpose over the shared t_kc / t_val arrays.  The triple product accumulates one column panel of C at a time, so
-// the slice of H^T it gathers from (a few tens of MB) stays L2 resident.
+// entries (r, x_rc) of column c with r in panel p, each stored as ONE packed 32-bit word in t_pk next to its value:
+// (r - first row of the panel) << 7 | (c & 127).  The low bits are all the banded-Q kernel needs of the column (its
+// weight tables span at most 96 consecutive columns), so an entry costs 12 bytes of the stream instead of 16.
+// t_ptr + p * X.cols is then the row-pointer array of panel p's transpose over the shared t_pk / t_val arrays.  The
+// triple product accumulates one column panel of C at a time, so the slice of H^T it gathers from (a few tens of MB)
+// stays L2 resident.
 template <int LANES>
 __global__ void __launch_bounds__(256)
 k_transpose_count_panels(Csr X, int row_begin, int row_end, int panel_w, int32_t* __restrict__ counts) {
@@ -348,11 +351,13 @@ k_transpose_count_panels(Csr X, int row_begin, int row_end, int panel_w, int32_t
 template <int LANES>
 __global__ void __launch_bounds__(256)
 k_transpose_fill_panels(Csr X, int row_begin, int row_end, int panel_w, const int32_t* __restrict__ t_ptr,
-                        int32_t* __restrict__ cursor, int2* __restrict__ t_kc, double* __restrict__ t_val) {
+                        int32_t* __restrict__ cursor, uint32_t* __restrict__ t_pk, double* __restrict__ t_val) {
     const int r = row_begin + (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const int gl = threadIdx.x % LANES;
     if (r >= row_end) return;
-    const size_t off = (size_t)((r - row_begin) / panel_w) * X.cols;
+    const int panel = (r - row_begin) / panel_w;
+    const size_t off = (size_t)panel * X.cols;
+    const uint32_t rel = (uint32_t)(r - row_begin - panel * panel_w) << kPanelColBits;
     const int s = __ldg(X.ptr + r), e = __ldg(X.ptr + r + 1);
     for (int p = s + gl; p < e; p += 2 * LANES) {
         const int p2 = p + LANES;
@@ -364,10 +369,10 @@ k_transpose_fill_panels(Csr X, int row_begin, int row_end, int panel_w, const in
         const int b1 = c1 >= 0 ? __ldg(t_ptr + off + c1) : 0;
         const int o0 = atomicAdd(cursor + off + c0, 1);
         const int o1 = c1 >= 0 ? atomicAdd(cursor + off + c1, 1) : 0;
-        t_kc[b0 + o0] = make_int2(r, c0);
+        t_pk[b0 + o0] = rel | ((uint32_t)c0 & kPanelColMask);
         t_val[b0 + o0] = v0;
         if (c1 >= 0) {
-            t_kc[b1 + o1] = make_int2(r, c1);
+            t_pk[b1 + o1] = rel | ((uint32_t)c1 & kPanelColMask);
             t_val[b1 + o1] = v1;
         }
     }
@@ -385,14 +390,14 @@ cudaError_t launch_transpose_count_panels(const LaunchCtx& lc, const Csr& X, int
     return cudaSuccess;
 }
 cudaError_t launch_transpose_fill_panels(const LaunchCtx& lc, const Csr& X, int64_t nnz, int row_begin, int row_end,
-                                         int panel_w, const int32_t* t_ptr, int32_t* d_cursor, int2* t_kc,
+                                         int panel_w, const int32_t* t_ptr, int32_t* d_cursor, uint32_t* t_pk,
                                          double* t_val) {
     const int rows = row_end - row_begin;
     if (rows <= 0) return cudaSuccess;
     if (nnz >= (int64_t)48 * X.rows)
-        k_transpose_fill_panels<32><<<(rows + 7) / 8, 256, 0, lc.stream>>>(X, row_begin, row_end, panel_w, t_ptr, d_cursor, t_kc, t_val);
+        k_transpose_fill_panels<32><<<(rows + 7) / 8, 256, 0, lc.stream>>>(X, row_begin, row_end, panel_w, t_ptr, d_cursor, t_pk, t_val);
     else
-        k_transpose_fill_panels<8><<<(rows + 31) / 32, 256, 0, lc.stream>>>(X, row_begin, row_end, panel_w, t_ptr, d_cursor, t_kc, t_val);
+        k_transpose_fill_panels<8><<<(rows + 31) / 32, 256, 0, lc.stream>>>(X, row_begin, row_end, panel_w, t_ptr, d_cursor, t_pk, t_val);
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
 }

@@ -720,11 +720,11 @@ int dense_rows(spgemm_b200_mat* a, spgemm_b200_mat* b_in, int upper_only, int r0
 // Paneled transpose of rows [plan.k0, n) of H (analysis.cu): one CSR with plan.np * H.cols rows.
 struct PanelT {
     int32_t* ptr = nullptr;
-    int2* kc = nullptr;            // (row of H, column of H) of every entry
+    uint32_t* pk = nullptr;        // packed (row of H within its panel, low bits of the column) of every entry
     double* val = nullptr;
 };
 static void panels_release(PanelT& t) {
-    dfree(t.ptr); dfree(t.kc); dfree(t.val);
+    dfree(t.ptr); dfree(t.pk); dfree(t.val);
     t = PanelT();
 }
 // A paneled transpose kept on its matrix (spgemm_b200_mat_cache_transpose): a caller that multiplies with the same H
@@ -746,11 +746,12 @@ static int transpose_panels(const spgemm_b200_mat* h, const TriplePlan& plan, Pa
     NvtxRange nv("spgemm_b200:transpose_panels");
     const size_t trows = (size_t)plan.np * (size_t)h->cols;
     if (trows + 1 > 0x7fffffffULL) return fail(SPGEMM_B200_ERR_OVERFLOW, "triple: panels x columns of H exceed 2^31");
+    if (plan.panel_w > kPanelMaxWidth) return fail(SPGEMM_B200_ERR_OVERFLOW, "triple: panel wider than the entry packing");
     PanelT t;
     int32_t *counts = nullptr, *cursor = nullptr;
     int64_t* tmp = nullptr;
     int rc;
-    if ((rc = dalloc(&t.ptr, trows + 1)) || (rc = dalloc(&t.kc, (size_t)h->nnz)) || (rc = dalloc(&t.val, (size_t)h->nnz)) ||
+    if ((rc = dalloc(&t.ptr, trows + 1)) || (rc = dalloc(&t.pk, (size_t)h->nnz)) || (rc = dalloc(&t.val, (size_t)h->nnz)) ||
         (rc = dalloc(&counts, trows + 1)) || (rc = dalloc(&cursor, trows + 1)) || (rc = dalloc(&tmp, 1032))) {
         panels_release(t); dfree(counts); dfree(cursor); dfree(tmp);
         return rc;
@@ -761,7 +762,7 @@ static int transpose_panels(const spgemm_b200_mat* h, const TriplePlan& plan, Pa
     if (e == cudaSuccess) e = launch_transpose_count_panels(lc, view(h), h->nnz, plan.k0, h->rows, plan.panel_w, counts);
     if (e == cudaSuccess) e = launch_scan_i32(lc, counts, t.ptr, (int)trows, tmp);
     if (e == cudaSuccess)
-        e = launch_transpose_fill_panels(lc, view(h), h->nnz, plan.k0, h->rows, plan.panel_w, t.ptr, cursor, t.kc, t.val);
+        e = launch_transpose_fill_panels(lc, view(h), h->nnz, plan.k0, h->rows, plan.panel_w, t.ptr, cursor, t.pk, t.val);
     dfree(counts); dfree(cursor); dfree(tmp);
     if (e != cudaSuccess) {
         panels_release(t);
@@ -775,7 +776,7 @@ static int transpose_panels(const spgemm_b200_mat* h, const TriplePlan& plan, Pa
 int triple_rows(const spgemm_b200_mat* h, const spgemm_b200_mat* q, const spgemm_b200_mat* ht, int upper_only, int r0,
                 int r1, double* d_c, unsigned long long* d_cnt) {
     Ctx& g = cx();
-    (void)ht;      // a plain CSR transpose cannot stand in for the panels: they store (row, column) pairs
+    (void)ht;      // a plain CSR transpose cannot stand in for the panels: they store packed (row, column) words
     cudaError_t e = cudaMemsetAsync(d_cnt, 0, 32, g.stream);
     if (e != cudaSuccess) return fail(SPGEMM_B200_ERR_CUDA, "triple counters", e);
     int rc;
@@ -797,7 +798,7 @@ int triple_rows(const spgemm_b200_mat* h, const spgemm_b200_mat* q, const spgemm
         mark(EV_ANALYSIS); mark(EV_SYMBOLIC);
         NvtxRange nv("spgemm_b200:triple");
         const bool q_runs = q->checked && q->runs && env_mode("SPGEMM_B200_TRIPLE_GENERIC") == 0;
-        e = launch_triple_panels(lctx(), view(h), view(q), q_runs, t.ptr, t.kc, t.val, plan, upper_only != 0, r0, r1 - r0,
+        e = launch_triple_panels(lctx(), view(h), view(q), q_runs, t.ptr, t.pk, t.val, plan, upper_only != 0, r0, r1 - r0,
                                  d_c, d_cnt);
         if (!kept) panels_release(t);
     }

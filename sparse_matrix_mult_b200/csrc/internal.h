@@ -60,7 +60,7 @@ cudaError_t launch_transpose_fill(const LaunchCtx& lc, const Csr& X, int64_t nnz
 cudaError_t launch_transpose_count_panels(const LaunchCtx& lc, const Csr& X, int64_t nnz, int row_begin, int row_end,
                                           int panel_w, int32_t* d_counts);
 cudaError_t launch_transpose_fill_panels(const LaunchCtx& lc, const Csr& X, int64_t nnz, int row_begin, int row_end,
-                                         int panel_w, const int32_t* t_ptr, int32_t* d_cursor, int2* t_kc,
+                                         int panel_w, const int32_t* t_ptr, int32_t* d_cursor, uint32_t* t_pk,
                                          double* t_val);
 
 // rows sorted by column (ascending or descending), in place, any row length; d_long_list: int32[rows + 1] scratch
@@ -110,11 +110,15 @@ cudaError_t dense_kernels_configure();
 struct TriplePlan {
     int k0, np, panel_w;
 };
+// An entry (r, c) of the paneled transpose is one 32-bit word: (r - first row of its panel) << 7 | (c & 127)
+constexpr int kPanelColBits = 7;
+constexpr uint32_t kPanelColMask = (1u << kPanelColBits) - 1u;
+constexpr int kPanelMaxWidth = 1 << (32 - kPanelColBits);        // rows of H per panel the packing can address
 TriplePlan triple_plan(int n, int row_begin, bool upper_only, int64_t h_nnz, int h_cols);
-// t_ptr / t_kc / t_val: paneled transpose of rows [plan.k0, n) of H (launch_transpose_*_panels); q_runs: every row
+// t_ptr / t_pk / t_val: paneled transpose of rows [plan.k0, n) of H (launch_transpose_*_panels); q_runs: every row
 // of Q is one run of consecutive, ascending columns (banded Q), which selects the lean kernel
 cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q, bool q_runs, const int32_t* t_ptr,
-                                 const int2* t_kc, const double* t_val, const TriplePlan& plan, bool upper_only,
+                                 const uint32_t* t_pk, const double* t_val, const TriplePlan& plan, bool upper_only,
                                  int row_begin, int nrows, double* d_c,
                                  unsigned long long* d_counters /* [4], zeroed: P1, P2, ticket, spare */);
 cudaError_t triple_kernels_configure();

@@ -102,7 +102,7 @@ struct StepB { int hs, he; double w; };          // hs == he: nothing to contrac
 
 template <bool UPPER>
 __global__ void __launch_bounds__(1024, 1)
-k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __restrict__ t_kc,
+k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const uint32_t* __restrict__ t_pk,
                 const double* __restrict__ t_val, TriplePlan plan, int row_begin, int nrows, int win_cap,
                 double* __restrict__ C, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -244,7 +244,7 @@ k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __r
                                 if (pp < L) {
                                     addr[u] = (int)pp + s_d[owner];
                                     wv[u] = s_w[owner];
-                                    k[u] = __ldg(t_kc + addr[u]).x;
+                                    k[u] = p0 + (int)(__ldg(t_pk + addr[u]) >> kPanelColBits);
                                 }
                             }
                         }
@@ -292,9 +292,10 @@ k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __r
 //     c0.. of H^T, whose rows are ADJACENT in the panel's CSR: their entries are the one contiguous range
 //     [t_ptr[c0], t_ptr[c0 + len]);
 //   * a warp takes one entry of H at a time: it puts the (up to 96) weights into its table in shared memory and
-//     streams the range with coalesced 128-byte loads of (k, c) pairs and values; entry (k, c, h_kc) adds
-//     w[c - c0] * h_kc into the segment -- the weight is looked up by the column stored WITH the entry, so there is
-//     no per-product bookkeeping at all (k_triple_panels spends ~100 instructions per 32 entries on finding owners);
+//     streams the range with coalesced loads of packed (k, c) words and values (12 bytes per entry); entry
+//     (k, c, h_kc) adds w[c - c0] * h_kc into the segment -- the weight is looked up by the low 7 bits of the column
+//     stored WITH the entry (a table spans at most 96 consecutive columns), so there is no per-product bookkeeping
+//     at all (k_triple_panels spends ~100 instructions per 32 entries on finding owners);
 //   * the metadata of all entries of H[i,:] (j, h_ij, extent of row j of Q, c0) is loaded by one thread per entry
 //     at the start of the item, so its three dependent gathers are paid once per item, not once per entry, and
 //     the weights of a warp's NEXT entry are in flight while it streams the current one.
@@ -316,9 +317,9 @@ __device__ __forceinline__ int ld_keep_i32(const int32_t* p, unsigned long long 
     asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ int2 ld_keep_i2(const int2* p, unsigned long long pol) {
-    int2 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+__device__ __forceinline__ uint32_t ld_keep_u32(const uint32_t* p, unsigned long long pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     return v;
 }
 __device__ __forceinline__ double ld_keep_f64(const double* p, unsigned long long pol) {
@@ -329,7 +330,7 @@ __device__ __forceinline__ double ld_keep_f64(const double* p, unsigned long lon
 
 template <bool UPPER>
 __global__ void __launch_bounds__(1024, 1)
-k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __restrict__ t_kc,
+k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const uint32_t* __restrict__ t_pk,
               const double* __restrict__ t_val, TriplePlan plan, int row_begin, int nrows, int win_cap,
               double* __restrict__ C, unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -424,36 +425,39 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const int2* __res
                     s_wt[lane + 32] = hv * q1;
                     s_wt[lane + 64] = hv * q2;
                     __syncwarp();
-                    const double* wt = s_wt - cb;              // weight of column c: wt[c]
-                    // the range [es, ee), 32 entries per step, as a rolling pipeline: the (k, c) pairs and values of the
-                    // next step are in flight while the current step is multiplied and added (ranges are ~100-200
+                    // weight of an entry: s_wt[(c - cb) mod 128], from the low column bits stored with the entry
+                    const uint32_t cbm = (uint32_t)cb & kPanelColMask;
+                    // the range [es, ee), 32 entries per step, as a rolling pipeline: the packed (k, c) words and values of
+                    // the next step are in flight while the current step is multiplied and added (ranges are ~100-200
                     // entries long: wider steps would leave most lanes of the last one idle)
                     int x = es + lane;
-                    const int2* pk = t_kc + x;
+                    const uint32_t* pk = t_pk + x;
                     const double* pv = t_val + x;
-                    int2 kc = x < ee ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
+                    uint32_t kc = x < ee ? ld_keep_u32(pk, keep) : 0u;
                     double v = x < ee ? ld_keep_f64(pv, keep) : 0.0;
-                    if (!filtered) {
+                    if (!filtered) {                       // lo == p0: the segment starts at the panel's first column
                         for (; x < ee; x += 32) {
                             pk += 32;
                             pv += 32;
                             const bool more = x + 32 < ee;
-                            const int2 kcn = more ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
+                            const uint32_t kcn = more ? ld_keep_u32(pk, keep) : 0u;
                             const double vn = more ? ld_keep_f64(pv, keep) : 0.0;
-                            atomicAdd(acc + (kc.x - lo), wt[kc.y] * v);
+                            atomicAdd(acc + (kc >> kPanelColBits), s_wt[(kc - cbm) & kPanelColMask] * v);
                             kc = kcn;
                             v = vn;
                         }
                         if (lane == 0) p2 += (unsigned)(ee - es);
                     } else {
+                        const uint32_t lo_rel = (uint32_t)(lo - p0);
                         for (; x < ee; x += 32) {
                             pk += 32;
                             pv += 32;
                             const bool more = x + 32 < ee;
-                            const int2 kcn = more ? ld_keep_i2(pk, keep) : make_int2(-1, 0);
+                            const uint32_t kcn = more ? ld_keep_u32(pk, keep) : 0u;
                             const double vn = more ? ld_keep_f64(pv, keep) : 0.0;
-                            if (kc.x >= lo) {
-                                atomicAdd(acc + (kc.x - lo), wt[kc.y] * v);
+                            const uint32_t krel = kc >> kPanelColBits;
+                            if (krel >= lo_rel) {
+                                atomicAdd(acc + (krel - lo_rel), s_wt[(kc - cbm) & kPanelColMask] * v);
                                 ++p2;
                             }
                             kc = kcn;
@@ -527,7 +531,7 @@ TriplePlan triple_plan(int n, int row_begin, bool upper_only, int64_t h_nnz, int
     const int cover = n - plan.k0 > 0 ? n - plan.k0 : 1;
     const int cap = triple_cap_max();
     int np = (cover + cap - 1) / cap;
-    const double covered_bytes = 16.0 * (double)h_nnz * (double)cover / (double)(n > 0 ? n : 1);
+    const double covered_bytes = 12.0 * (double)h_nnz * (double)cover / (double)(n > 0 ? n : 1);
     const double budget = 1.0e6 * env_int("SPGEMM_B200_TRIPLE_L2_MB", 40) - 4.0 * (double)h_cols;
     if (budget > 0) {
         const int np_l2 = (int)(covered_bytes / budget) + 1;
@@ -545,7 +549,7 @@ TriplePlan triple_plan(int n, int row_begin, bool upper_only, int64_t h_nnz, int
 }
 
 cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q, bool q_runs, const int32_t* t_ptr,
-                                 const int2* t_kc, const double* t_val, const TriplePlan& plan, bool upper_only,
+                                 const uint32_t* t_pk, const double* t_val, const TriplePlan& plan, bool upper_only,
                                  int row_begin, int nrows, double* d_c, unsigned long long* d_counters) {
     const int n = H.rows;
     if (nrows <= 0 || n <= 0) return cudaSuccess;
@@ -571,14 +575,14 @@ cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q
     const size_t smem = smem_of(threads);
     if (q_runs) {
         if (upper_only)
-            k_triple_runs<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
+            k_triple_runs<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_pk, t_val, plan, row_begin, nrows, win, d_c, d_counters);
         else
-            k_triple_runs<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
+            k_triple_runs<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_pk, t_val, plan, row_begin, nrows, win, d_c, d_counters);
     } else {
         if (upper_only)
-            k_triple_panels<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
+            k_triple_panels<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_pk, t_val, plan, row_begin, nrows, win, d_c, d_counters);
         else
-            k_triple_panels<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_kc, t_val, plan, row_begin, nrows, win, d_c, d_counters);
+            k_triple_panels<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_pk, t_val, plan, row_begin, nrows, win, d_c, d_counters);
     }
     SB_LAUNCH_CHECK(lc);
     return cudaSuccess;
