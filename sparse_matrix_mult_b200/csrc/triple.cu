@@ -523,8 +523,10 @@ static int triple_cap_max() {
 }
 
 // Panels of C for rows [row_begin, ...): as few as the shared-memory accumulator allows (a panel is one segment), more
-// when the part of H^T they gather from would not stay in L2 (SPGEMM_B200_TRIPLE_L2_MB, default 40: the data is shared
-// by the SMs of both dies, so about half of the 126 MB is usable); SPGEMM_B200_TRIPLE_PANELS forces a count.
+// when the part of H^T they gather from would not stay in L2 (SPGEMM_B200_TRIPLE_L2_MB, default 32 for the 12-byte
+// entries and the row pointers of one panel: the data is shared by the SMs of both dies and the streams of Q and C pass
+// through beside it; cfg 5 measured 15.1 / 13.9 / 14.0 ms with panels of 32 / 24 / 19 MB); SPGEMM_B200_TRIPLE_PANELS
+// forces a count.
 TriplePlan triple_plan(int n, int row_begin, bool upper_only, int64_t h_nnz, int h_cols) {
     TriplePlan plan;
     plan.k0 = upper_only ? row_begin : 0;
@@ -532,7 +534,7 @@ TriplePlan triple_plan(int n, int row_begin, bool upper_only, int64_t h_nnz, int
     const int cap = triple_cap_max();
     int np = (cover + cap - 1) / cap;
     const double covered_bytes = 12.0 * (double)h_nnz * (double)cover / (double)(n > 0 ? n : 1);
-    const double budget = 1.0e6 * env_int("SPGEMM_B200_TRIPLE_L2_MB", 40) - 4.0 * (double)h_cols;
+    const double budget = 1.0e6 * env_int("SPGEMM_B200_TRIPLE_L2_MB", 32) - 4.0 * (double)h_cols;
     if (budget > 0) {
         const int np_l2 = (int)(covered_bytes / budget) + 1;
         if (np_l2 > np) np = np_l2;
