@@ -252,6 +252,8 @@ struct HostCache {
     std::mutex mu;
     std::multimap<size_t, void*> free_list;
     std::unordered_map<void*, size_t> sizes;
+    std::unordered_map<void*, uint64_t> freed_at;            // cached buffers: when they came back (eviction order)
+    uint64_t clock = 0;
     size_t cached = 0;
     // Keeps the buffers of the most recent results for reuse: up to `limit` bytes in total, or -- when a single
     // freed buffer is larger than that -- that one buffer alone (so a loop over the same product never pays
@@ -273,6 +275,7 @@ void* host_cache_alloc(size_t bytes) {
             void* p = it->second;
             g_host.cached -= it->first;
             g_host.free_list.erase(it);
+            g_host.freed_at.erase(p);
             return p;
         }
     }
@@ -304,15 +307,20 @@ void host_cache_free(void* p) {
             drop.push_back(p);
         } else {
             const size_t budget = size > g_host.limit ? size : g_host.limit;
-            // make room: evict the smallest cached buffers first
+            // make room: evict the buffers that came back longest ago first (the results of an earlier, different
+            // product; evicting by size instead kept a large stale buffer and dropped the ones the loop reuses)
             while (!g_host.free_list.empty() && g_host.cached + size > budget) {
                 auto victim = g_host.free_list.begin();
+                for (auto c = g_host.free_list.begin(); c != g_host.free_list.end(); ++c)
+                    if (g_host.freed_at[c->second] < g_host.freed_at[victim->second]) victim = c;
                 g_host.cached -= victim->first;
                 g_host.sizes.erase(victim->second);
+                g_host.freed_at.erase(victim->second);
                 drop.push_back(victim->second);
                 g_host.free_list.erase(victim);
             }
             g_host.free_list.emplace(size, p);
+            g_host.freed_at[p] = ++g_host.clock;
             g_host.cached += size;
         }
     }
@@ -325,6 +333,7 @@ void host_cache_clear() {
         std::lock_guard<std::mutex> hl(g_host.mu);
         for (auto& kv : g_host.free_list) { drop.push_back(kv.second); g_host.sizes.erase(kv.second); }
         g_host.free_list.clear();
+        g_host.freed_at.clear();
         g_host.cached = 0;
     }
     for (void* q : drop) cudaFreeHost(q);
