@@ -299,10 +299,11 @@ k_triple_panels(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const uint32_t*
 //   * the metadata of all entries of H[i,:] (j, h_ij, extent of row j of Q, c0) is loaded by one thread per entry
 //     at the start of the item, so its three dependent gathers are paid once per item, not once per entry, and
 //     the weights of a warp's NEXT entry are in flight while it streams the current one.
-// Dynamic shared memory: acc[win_cap] | hv[nt] | wt[nwarp * 96] | qs[nt] | len[nt] | c0[nt].
+// Dynamic shared memory: acc[win_cap] | hv[nt] | wt[nwarp * 96] | meta[nt] (int4: start of row j of Q, its length, its
+// first column).
 constexpr int kRunPiece = 96;                    // columns of a run handled per pass of the weight table
 __host__ __device__ inline size_t triple_runs_smem(int win_cap, int threads) {
-    return (size_t)win_cap * 8 + (size_t)threads * 44 + 16;
+    return (size_t)win_cap * 8 + (size_t)threads * 48 + 16;
 }
 
 // Loads of the panel of H^T carry an L2 evict_last policy: the panel (a few tens of MB) is what every block gathers
@@ -341,9 +342,7 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const uint32_t* _
     double* acc = reinterpret_cast<double*>(s_raw);
     double* s_hv = acc + win_cap;
     double* s_wt = s_hv + nt + warp * kRunPiece;                    // this warp's 96 weights
-    int* s_qs = reinterpret_cast<int*>(s_hv + 4 * nt);              // nwarp * 96 == 3 * nt
-    int* s_len = s_qs + nt;
-    int* s_c0 = s_len + nt;
+    int4* s_meta = reinterpret_cast<int4*>(s_hv + 4 * nt);          // nwarp * 96 == 3 * nt; 16-byte aligned
     const unsigned long long keep = l2_keep_policy();
     if (tid < 2) S.cnt[tid] = 0;
     for (int t = tid; t < win_cap; t += nt) acc[t] = 0.0;
@@ -378,9 +377,7 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const uint32_t* _
                 const int qs = __ldg(Q.ptr + j);
                 const int len = __ldg(Q.ptr + j + 1) - qs;
                 s_hv[tid] = __ldg(H.val + base + tid);
-                s_qs[tid] = qs;
-                s_len[tid] = len;
-                s_c0[tid] = len > 0 ? __ldg(Q.idx + qs) : 0;
+                s_meta[tid] = make_int4(qs, len, len > 0 ? __ldg(Q.idx + qs) : 0, 0);
                 if (first_panel) p1 += (unsigned)len;
             }
             __syncthreads();
@@ -388,12 +385,16 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const uint32_t* _
             // values q_{j,c} of entry e + nwarp and the bounds of its range of H^T are already in flight.
             const bool filtered = UPPER && lo > p0;        // the panel holds the diagonal: entries k < i are skipped
             int e = warp;
-            double nq0 = 0.0, nq1 = 0.0, nq2 = 0.0;
+            double nq0 = 0.0, nq1 = 0.0, nq2 = 0.0, nhv = 0.0;
             int nes = 0, nee = 0;
+            int4 nm = make_int4(0, 0, 0, 0);               // metadata of the prefetched entry: one 128-bit broadcast load
             auto prefetch = [&](int en) {
-                nq0 = 0.0; nq1 = 0.0; nq2 = 0.0; nes = 0; nee = 0;
+                nq0 = 0.0; nq1 = 0.0; nq2 = 0.0; nes = 0; nee = 0; nhv = 0.0;
+                nm = make_int4(0, 0, 0, 0);
                 if (en < cnt) {
-                    const int nlen = s_len[en], nqs = s_qs[en], nc0 = s_c0[en];
+                    nm = s_meta[en];
+                    nhv = s_hv[en];
+                    const int nlen = nm.y, nqs = nm.x, nc0 = nm.z;
                     if (lane < nlen) nq0 = __ldcs(Q.val + nqs + lane);
                     if (lane + 32 < nlen) nq1 = __ldcs(Q.val + nqs + lane + 32);
                     if (lane + 64 < nlen) nq2 = __ldcs(Q.val + nqs + lane + 64);
@@ -405,8 +406,8 @@ k_triple_runs(Csr H, Csr Q, const int32_t* __restrict__ t_ptr, const uint32_t* _
             };
             prefetch(e);
             for (; e < cnt; e += nwarp) {
-                const int len = s_len[e], qs = s_qs[e], c0 = s_c0[e];
-                const double hv = s_hv[e];
+                const int len = nm.y, qs = nm.x, c0 = nm.z;    // entry e was prefetched: its metadata is in registers
+                const double hv = nhv;
                 for (int t0 = 0; t0 < len; t0 += kRunPiece) {
                     const int cn = min(kRunPiece, len - t0);
                     const int cb = c0 + t0;
