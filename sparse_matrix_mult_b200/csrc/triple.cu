@@ -579,7 +579,7 @@ cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q
     if (grid < 1) grid = 1;
     const size_t smem = smem_of(threads);
     if (q_runs) {
-if (upper_only)
+        if (upper_only)
             k_triple_runs<true><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_pk, t_val, plan, row_begin, nrows, win, d_c, d_counters);
         else
             k_triple_runs<false><<<grid, threads, smem, lc.stream>>>(H, Q, t_ptr, t_pk, t_val, plan, row_begin, nrows, win, d_c, d_counters);
