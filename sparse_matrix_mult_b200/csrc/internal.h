@@ -120,7 +120,8 @@ TriplePlan triple_plan(int n, int row_begin, bool upper_only, int64_t h_nnz, int
 cudaError_t launch_triple_panels(const LaunchCtx& lc, const Csr& H, const Csr& Q, bool q_runs, const int32_t* t_ptr,
                                  const uint32_t* t_pk, const double* t_val, const TriplePlan& plan, bool upper_only,
                                  int row_begin, int nrows, double* d_c,
-                                 unsigned long long* d_counters /* [4], zeroed: P1, P2, ticket, spare */);
+                                 unsigned long long* d_counters /* [4], zeroed: P1, P2, ticket, spare */,
+                                 int4* d_entry_meta /* nnz(H) entries of workspace for the banded-Q kernel, or null */);
 cudaError_t triple_kernels_configure();
 
 }  // namespace sb
