@@ -14,7 +14,7 @@
 //                    contiguous range of H^T per entry of H and looks the weight up by the column stored with the entry
 //   k_triple_panels  any Q: the rows of H^T of 32 products at a time are walked as one flat, balanced stream
 // (The round-1 kernel -- a row of C in global memory, every add an L2 reduction, one gather walk per thread -- measured
-//  23.2 ms on cfg 5 against 13.3 ms / 21.6 ms for these two: profiles/r2/SUMMARY.md.)
+//  23.2 ms on cfg 5 against 12.4 ms / 21.6 ms for these two: profiles/r2/SUMMARY.md.)
 #include <cstdlib>
 
 #include "internal.h"
